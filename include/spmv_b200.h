@@ -1,0 +1,117 @@
+/*
+ * spmv_b200.h -- non-breaking extensions next to the drop-in API of spmv.h.
+ *
+ * Nothing here exists in the reference; a client that only knows spmv.h never needs it.  These entry
+ * points cover what moving the path to a GPU adds: stream control for device-resident x/y, error
+ * retrieval (the reference API returns void everywhere), introspection of the device layouts for
+ * bit-exact structure tests, the equal-nnz row partition used to shard a matrix across GPUs, and
+ * on-device synthetic matrix generators so that multi-GB benchmark matrices never cross PCIe.
+ *
+ * Plain C ABI: pointers, sizes, ints.  No CUDA or torch types appear in any signature (a CUDA stream
+ * is passed as void*).
+ */
+#ifndef SPMV_B200_EXT_H
+#define SPMV_B200_EXT_H
+#include <stddef.h>
+#include "spmv.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define SPMV_B200_VERSION 100 /* round 1 */
+
+/* ---- errors ------------------------------------------------------------------------------------
+ * The reference swallows every error (common.c:136,285; csr5_spmv.cpp:31-35).  Same void API here,
+ * plus: the last failure message of the calling thread ("" when none). */
+SPMV_B200_API int spmv_b200_version(void);
+SPMV_B200_API const char *spmv_b200_last_error(void);
+SPMV_B200_API void spmv_b200_clear_error(void);
+
+/* ---- streams -----------------------------------------------------------------------------------
+ * spmv() with HOST x/y is synchronous (reference semantics).  With DEVICE x/y it is enqueued on the
+ * handle's stream (default: the legacy default stream 0) and returns immediately. */
+SPMV_B200_API void spmv_b200_set_stream(spmv_Handle_t handle, void *cuda_stream);
+SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
+
+/* ---- options (process-global, read when a handle is created) --------------------------------------
+ * Also settable through the environment as SPMV_B200_<KEY IN CAPITALS>.  Keys:
+ *   "sell_sigma"      sorting window of Method_SellCSigma (multiple of 32, <= 4096; default 256)
+ *   "csr5_sigma"      nnz per lane of a CSR5 tile (4..16; default 16)
+ *   "block_nnz"       nnz per row block of Method_Balanced (default 512)
+ *   "tile_items"      items per thread of the merge-path / equal-nnz tiles (4..16; default 8)
+ *   "tpr"             force threads-per-row of Method_Parallel (power of two <= 32; 0 = from mean)
+ *   "x_bands"         column bands for x locality in Method_Parallel (0 = automatic, 1 = off)
+ * Returns 0, or -1 for an unknown key. */
+SPMV_B200_API int spmv_b200_set_option(const char *key, long long value);
+SPMV_B200_API long long spmv_b200_get_option(const char *key);
+
+/* ---- introspection -----------------------------------------------------------------------------
+ * spmv_b200_info: scalar facts about a handle.  Keys: "kernel" (internal kernel family, see
+ * SPMV_B200_KERNEL_*), "requested", "m", "n", "nnz", "tpr", "parts", "tiles", "sigma", "banner",
+ * "slices", "padded_nnz", "csr5_p", "csr5_sigma", "csr5_num_offsets", "csr5_tail_start", "device",
+ * "has_empty_rows", "x_bands", "owns_csr".  Returns -1 for an unknown key / NULL handle.
+ *
+ * spmv_b200_structure: copy a device layout array to HOST memory.  Returns its size in bytes (call
+ * with dst = NULL to size it), or -1.  Names: "splitter" (int[parts+1], a9), "ref_splitter"
+ * (int[nthreads+1], a9 with the caller's nthreads), "tile_rows" (int[tiles+1]), "merge_coords"
+ * (int[2*(tiles+1)]), "sell_perm" (int[banner], a13), "sell_width" (int[slices]), "sell_slice_ptr"
+ * (long long[slices+1]), "sell_col" (int[padded]), "sell_val", "csr5_tile_ptr" (unsigned[p+1], a16),
+ * "csr5_tile_desc" (unsigned[p*32], a17), "csr5_offset_ptr" (int[p+1]), "csr5_offsets" (int[num]),
+ * "csr5_col" (int[nnz], a18), "csr5_val". */
+enum {
+    SPMV_B200_KERNEL_NONE = 0,
+    SPMV_B200_KERNEL_CSR_REFORDER = 1, /* Method_Serial   */
+    SPMV_B200_KERNEL_CSR_VECTOR = 2,   /* Method_Parallel */
+    SPMV_B200_KERNEL_ROW_BLOCKS = 3,   /* Method_Balanced */
+    SPMV_B200_KERNEL_MERGE_PATH = 4,   /* Method_Balanced2 */
+    SPMV_B200_KERNEL_NNZ_SPLIT = 5,    /* Method_Balanced_Yid */
+    SPMV_B200_KERNEL_SELL = 6,         /* Method_SellCSigma */
+    SPMV_B200_KERNEL_CSR5 = 7,         /* Method_CSR5SPMV */
+    SPMV_B200_KERNEL_CSR_BANDED = 8    /* Method_Parallel with column bands */
+};
+SPMV_B200_API long long spmv_b200_info(spmv_Handle_t handle, const char *key);
+SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes);
+
+/* kernels launched by this process on the spmv() path since load (for benchmark accounting) */
+SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
+
+/* ---- multi-GPU row partition -------------------------------------------------------------------
+ * splitter[g] = right_boundary(RowPtr, min(g*ceil(nnz/parts), nnz), m+1) - 1, g = 0..parts: the
+ * reference's init_csrSplitter_balanced2 (parallel_balanced2_spmv.c:41-53) with nthreads = parts.
+ * RowPtr is a HOST pointer; pure host code, usable without a GPU.  Returns 0 or -1. */
+SPMV_B200_API int spmv_b200_partition_rows(const int *RowPtr, int m, int parts, int *splitter_out);
+
+/* ---- device memory helpers for C clients (Python clients use torch tensors) ----------------------- */
+SPMV_B200_API void *spmv_b200_malloc(size_t bytes);
+SPMV_B200_API void spmv_b200_free(void *device_ptr);
+/* kind: 0 host->device, 1 device->host, 2 device->device; synchronous.  Returns 0 or -1. */
+SPMV_B200_API int spmv_b200_memcpy(void *dst, const void *src, size_t bytes, int kind);
+
+/* ---- on-device synthetic matrices (bit-identical to spmv_b200/matrices.py) ----------
+ * Each fills *out with DEVICE pointers owned by the caller (release with spmv_b200_csr_free).
+ * `size` = sizeof(double) or sizeof(float).  Returns 0 or -1 (see spmv_b200_last_error). */
+typedef struct spmv_b200_csr {
+    int m, n;
+    long long nnz;
+    int *RowPtr;
+    int *ColIdx;
+    void *Val;
+    unsigned long size;
+} spmv_b200_csr;
+
+SPMV_B200_API int spmv_b200_gen_laplacian2d(int nx, int ny, unsigned long size, spmv_b200_csr *out);
+SPMV_B200_API int spmv_b200_gen_stencil27(int nx, int ny, int nz, unsigned long size, spmv_b200_csr *out);
+/* rows [row0, row0+m) of the global uniform-random matrix with k entries per row over n columns */
+SPMV_B200_API int spmv_b200_gen_uniform(int m, int n, int k, unsigned long long seed, long long row0, int eighths,
+                          unsigned long size, spmv_b200_csr *out);
+SPMV_B200_API int spmv_b200_gen_rmat(int scale, int edge_factor, unsigned long long seed, unsigned long size,
+                       spmv_b200_csr *out);
+/* x_j for j in [0, n): 0.5 + (hash(j) mod 1000)/1000, or all ones */
+SPMV_B200_API int spmv_b200_gen_x(void *device_dst, long long n, unsigned long long seed, int ones, unsigned long size);
+SPMV_B200_API void spmv_b200_csr_free(spmv_b200_csr *csr);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* SPMV_B200_EXT_H */

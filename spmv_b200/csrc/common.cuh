@@ -1,0 +1,233 @@
+// common.cuh -- device state, error latch, and the sm_100a load/store + warp primitives shared by all
+// kernel families of libspmv_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define SPMV_B200_NO_HOST_HEADERS 1
+#include "../../include/spmv_b200.h"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------
+// error latch (the public API returns void, reference include/spmv.h)
+// ------------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+#define SB_CUDA(expr) ::sb::cuda_ok((expr), #expr, __FILE__, __LINE__)
+#define SB_TRY(expr) do { if (!SB_CUDA(expr)) return false; } while (0)
+
+void count_launch(int n = 1);
+
+constexpr int kThreads = 256;       // CTA size of every spmv-path kernel
+constexpr int kWarpsPerCta = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident state hanging off spmv_Handle::extraHandle.
+// ------------------------------------------------------------------------------------------------
+struct DeviceState {
+    uint32_t magic = 0x5b200a11u;
+    int device = 0;
+    cudaStream_t stream = nullptr;  // legacy default stream unless spmv_b200_set_stream
+    int m = 0, n = 0, nnz = 0;
+    int vsize = 8;                  // 8 = fp64, 4 = fp32
+    int requested = 0;              // SPMV_METHODS asked for at create
+    int kernel = SPMV_B200_KERNEL_NONE;
+    bool ok = false;                // false => spmv() is a no-op
+    bool has_empty_rows = false;
+    bool vec_ok = true;             // ColIdx / Val 32-byte aligned: 128/256-bit loads allowed
+
+    // CSR on the device (owned upload, or the caller's device arrays adopted in place)
+    int *rowptr = nullptr, *col = nullptr;
+    void *val = nullptr;
+    bool owns_csr = false;
+
+    // staging for host-side x / y
+    void *x_stage = nullptr, *y_stage = nullptr;
+
+    // Method_Parallel
+    int tpr = 0;
+    // column bands (CSR_BANDED): band b covers columns [b*band_cols, (b+1)*band_cols)
+    int x_bands = 1, band_cols = 0;
+    int *band_ptr = nullptr;        // int[x_bands * m + 1] : per (band,row) start into col/val
+    // Method_Balanced: row blocks; ref_splitter mirrors the reference with the caller's nthreads
+    int parts = 0;
+    int *splitter = nullptr, *ref_splitter = nullptr;
+    int ref_T = 0;
+    // Method_Balanced2 / Method_Balanced_Yid: tiles + carries
+    int tiles = 0, tile_items = 0;
+    int *tile_rows = nullptr;       // nnz-split: row containing the first nnz of each tile [tiles+1]
+    int2 *merge_coords = nullptr;   // merge-path: (row, nnz) start of each tile [tiles+1]
+    void *carry_val = nullptr;      // [tiles] partial sum that belongs to a row started earlier
+    int *carry_row = nullptr;       // [tiles] that row, or -1
+    // Method_SellCSigma
+    int sigma = 0, banner = 0, slices = 0;
+    long long padded = 0;
+    int *sell_perm = nullptr, *sell_width = nullptr, *sell_full = nullptr, *sell_col = nullptr;
+    long long *sell_slice_ptr = nullptr;
+    void *sell_val = nullptr;
+    // Method_CSR5SPMV (omega = 32)
+    int c5_sigma = 0, c5_p = 0, c5_bit_y = 0, c5_bit_ss = 0, c5_num_offsets = 0, c5_tail_start = 0;
+    uint32_t *c5_tile_ptr = nullptr, *c5_tile_desc = nullptr;
+    int *c5_off_ptr = nullptr, *c5_off = nullptr, *c5_col = nullptr;
+    void *c5_val = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// sm_100a memory primitives.
+//  * matrix streams (ColIdx / Val) are read exactly once per SpMV: non-coherent path, no L1
+//    allocation, L2 evict-first -- 256-bit LDG.E.NA.EFL2.256 where alignment allows;
+//  * x is the only re-used operand: read-only path with an L2 evict-last policy so the streams do
+//    not push it out of the 126 MB L2.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// ---- gathers from x (evict-last) ----
+__device__ __forceinline__ double ldg_x(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_x(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// ---- scalar streaming loads ----
+__device__ __forceinline__ int ldg_stream(const int *p)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ldg_stream(const double *p)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// ---- scalar streaming loads with an explicit L2 policy (evict-first for the matrix streams) ----
+__device__ __forceinline__ int ldg_stream(const int *p, uint64_t pol)
+{
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ldg_stream(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// ---- 4-element chunk loads (element index multiple of 4; base 32-byte aligned) ----
+__device__ __forceinline__ void ldg_stream4(const int *p, int (&r)[4], uint64_t pol)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ldg_stream4(const float *p, float (&r)[4], uint64_t pol)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ldg_stream4(const double *p, double (&r)[4], uint64_t)
+{
+    unsigned long long a, b, c, d;  // one 256-bit load, L2 evict-first encoded in the instruction
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    r[0] = __longlong_as_double((long long)a);
+    r[1] = __longlong_as_double((long long)b);
+    r[2] = __longlong_as_double((long long)c);
+    r[3] = __longlong_as_double((long long)d);
+}
+// ---- 8-element chunk loads (element index multiple of 8; 256-bit for 4-byte types) ----
+__device__ __forceinline__ void ldg_stream8(const int *p, int (&r)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream8(const float *p, float (&r)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(p));
+}
+
+// ---- y stores: written once, never re-read by the kernel ----
+__device__ __forceinline__ void stg_y(double *p, double v)
+{
+    asm volatile("st.global.L1::no_allocate.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void stg_y(float *p, float v)
+{
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+
+// sub-warp butterfly sum over `width` lanes (power of two); every lane of the group gets the total
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, int width)
+{
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+template <typename T, int WIDTH>
+__device__ __forceinline__ T group_sum_c(T v)
+{
+#pragma unroll
+    for (int o = WIDTH >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// number of entries of a[0..size) that are <= key: the reference's
+// binary_search_right_boundary_kernel (parallel_balanced_spmv.c:17-37), usable on host and device.
+__host__ __device__ __forceinline__ int right_boundary(const int *a, int key, int size)
+{
+    int start = 0, stop = size - 1;
+    while (stop >= start) {
+        const int median = (int)(((long long)stop + start) >> 1);
+        if (key >= a[median]) start = median + 1; else stop = median - 1;
+    }
+    return start;
+}
+#endif  // __CUDACC__
+
+}  // namespace sb

@@ -1,0 +1,267 @@
+// csr_kernels.cuh -- kernels that work directly on the CSR arrays:
+//   csr_reforder_kernel   Method_Serial    (bit-identical summation order to the reference)
+//   csr_vector_kernel     Method_Parallel  (sub-warp per row, 128/256-bit streaming loads)
+//   row_block_kernel      Method_Balanced  (one warp per nnz-balanced row block of the csrSplitter)
+//   csr_banded_kernel     Method_Parallel with column bands (x band kept L2-resident)
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------
+// Method_Serial.  Replaces spmv_serial_cpp_{d,s} (reference src/src_spmv/serial_spmv.c:9-37) and
+// Dot_Product_Avx2_{d,s} (inner_spmv.h:232-354).  The AVX2 register becomes a group of L lanes
+// (L = 4 for fp64, 8 for fp32): lane l owns elements l, l+L, ... as an FMA chain from +0, the
+// horizontal add is the same tree ((l0+l1)+(l2+l3) resp. ((l0+l4)+(l2+l6))+((l1+l5)+(l3+l7))) done
+// with xor-shuffles, and lane 0 folds in the len%L tail exactly as the reference's compiled remainder
+// loop does (see oracle/spmv_oracle.c row_dot_s for the fp32 in-order 4-wide step).  Result: y is
+// bitwise equal to the reference's Method_Serial.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+csr_reforder_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ col,
+                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y)
+{
+    constexpr int L = sizeof(T) == 8 ? 4 : 8;
+    const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long row_l = gt / L;
+    const int lane = threadIdx.x & (L - 1);
+    const bool valid = row_l < m;
+    const int row = valid ? (int)row_l : 0;
+    const int start = valid ? rowptr[row] : 0;
+    const int end = valid ? rowptr[row + 1] : 0;
+    const int len = end - start;
+    const int groups = len / L;
+
+    T acc = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int j = start + g * L + lane;
+        acc = fma_t(val[j], x[col[j]], acc);
+    }
+    if (L == 4) {
+        acc += __shfl_xor_sync(kFull, acc, 1);
+        acc += __shfl_xor_sync(kFull, acc, 2);
+    } else {
+        acc += __shfl_xor_sync(kFull, acc, 4);
+        acc += __shfl_xor_sync(kFull, acc, 2);
+        acc += __shfl_xor_sync(kFull, acc, 1);
+    }
+    if (valid && lane == 0) {
+        T result = acc;  // all lanes are +0 when groups == 0, and (+0)+(+0) = +0 as in the reference
+        int j = start + groups * L;
+        if (sizeof(T) == 4 && end - j >= 4) {
+            // the pinned reference build adds four UNFUSED products in order here
+            float p0 = __fmul_rn((float)val[j], (float)x[col[j]]);
+            float p1 = __fmul_rn((float)val[j + 1], (float)x[col[j + 1]]);
+            float p2 = __fmul_rn((float)val[j + 2], (float)x[col[j + 2]]);
+            float p3 = __fmul_rn((float)val[j + 3], (float)x[col[j + 3]]);
+            float r = (float)result;
+            r = __fadd_rn(r, p0);
+            r = __fadd_rn(r, p1);
+            r = __fadd_rn(r, p2);
+            r = __fadd_rn(r, p3);
+            result = (T)r;
+            j += 4;
+        }
+        for (; j < end; ++j) result = fma_t(val[j], x[col[j]], result);
+        y[row] = result;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One row, cooperatively by `tpr` lanes, in 4-element chunks aligned to 4 elements so that ColIdx is
+// read with one 128-bit and Val with one 128/256-bit streaming load per lane and chunk.  Elements of
+// a chunk that belong to the neighbouring rows are masked out (they sit in sectors this warp fetches
+// anyway).  The last partial chunk of the whole array is read element-wise (no read past nnz).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, int nnz4,
+                                         const int *__restrict__ col, const T *__restrict__ val,
+                                         const T *__restrict__ x, uint64_t pl, uint64_t pf)
+{
+    T sum = 0;
+    if (VEC) {
+#pragma unroll 2
+        for (int j = (start & ~3) + 4 * sl; j < end; j += 4 * tpr) {
+            if (j < nnz4) {
+                int c[4];
+                T v[4];
+                ldg_stream4(col + j, c, pf);
+                ldg_stream4(val + j, v, pf);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int jj = j + k;
+                    if (jj >= start && jj < end) sum = fma_t(v[k], ldg_x(x + c[k], pl), sum);
+                }
+            } else {
+                for (int k = 0; k < 4; ++k) {
+                    const int jj = j + k;
+                    if (jj >= start && jj < end)
+                        sum = fma_t(ldg_stream(val + jj), ldg_x(x + ldg_stream(col + jj), pl), sum);
+                }
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int j = start + sl; j < end; j += tpr)
+            sum = fma_t(ldg_stream(val + j), ldg_x(x + ldg_stream(col + j), pl), sum);
+    }
+    return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Method_Parallel.  Replaces spmv_parallel_cpp_{d,s} (reference src/src_spmv/parallel_spmv.c:5-34):
+// the OpenMP row loop becomes a grid of sub-warps, TPR lanes per row with TPR = 2^k ~ mean row
+// length / 4 chosen at create.  Fixed butterfly reduction => bitwise reproducible.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TPR, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__restrict__ col,
+                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y)
+{
+    const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
+    const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long row_l = gt / TPR;
+    const int sl = threadIdx.x & (TPR - 1);
+    const bool valid = row_l < m;
+    const int row = valid ? (int)row_l : 0;
+    const int start = valid ? rowptr[row] : 0;
+    const int end = valid ? rowptr[row + 1] : 0;
+    T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
+    sum = group_sum_c<T, TPR>(sum);
+    if (valid && sl == 0) stg_y(y + row, sum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Method_Balanced.  Replaces spmv_parallel_balanced_cpp_{d,s} (reference
+// src/src_spmv/parallel_balanced_spmv.c:77-125): "thread t does rows csrSplitter[t]..csrSplitter[t+1]"
+// with the thread replaced by a warp and T = number of row blocks (~block_nnz non-zeros each, the
+// same a9 splitter formula).  Inside its block the warp picks lanes-per-row from the block's own
+// mean row length, so short-row and long-row regions of one matrix each get a fitting geometry.
+// Block 0 starts at row 0 (the reference leaves leading empty rows unwritten).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int *__restrict__ rowptr,
+                 const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
+                 T *__restrict__ y)
+{
+    const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
+    const int w = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= parts) return;
+    const int r0 = w == 0 ? 0 : splitter[w];
+    const int r1 = splitter[w + 1];
+    const int nrows = r1 - r0;
+    if (nrows <= 0) return;
+    const int nz = rowptr[r1] - rowptr[r0];
+    const int avg = (nz + nrows - 1) / nrows;
+    int tpr = 1;
+    while (tpr < 32 && 4 * tpr < avg) tpr <<= 1;
+    const int rows_per_iter = 32 / tpr;
+    const int sub = lane / tpr, sl = lane & (tpr - 1);
+    const int nnz4 = nnz & ~3;
+    for (int base = r0; base < r1; base += rows_per_iter) {
+        const int row = base + sub;
+        const bool valid = row < r1;
+        const int start = valid ? rowptr[row] : 0;
+        const int end = valid ? rowptr[row + 1] : 0;
+        T sum = row_partial<T, VEC>(start, end, sl, tpr, nnz4, col, val, x, pl, pf);
+        sum = group_sum(sum, tpr);
+        if (valid && sl == 0) stg_y(y + row, sum);
+    }
+}
+
+// a9: csrSplitter of init_csrSplitter_balanced2 (reference parallel_balanced2_spmv.c:41-53).
+__global__ void splitter_kernel(int parts, int nnz, int m, const int *__restrict__ rowptr,
+                                int *__restrict__ splitter)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > parts) return;
+    const long long stride = ((long long)nnz + parts - 1) / parts;
+    long long b = (long long)t * stride;
+    if (b > nnz) b = nnz;
+    splitter[t] = right_boundary(rowptr, (int)b, m + 1) - 1;
+}
+
+// a10: the Yid scan of parallel_balanced2_get_handle (parallel_balanced2_spmv.c:72-90), reduced to
+// the one bit that decides Balanced vs Balanced2: does any partition own no whole row?
+__global__ void splitter_starved_kernel(int parts, int m, const int *__restrict__ splitter,
+                                        int *__restrict__ flag)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= parts) return;
+    if (splitter[t + 1] == splitter[t] && splitter[t] != m) *flag = 1;
+}
+
+__global__ void empty_rows_kernel(int m, const int *__restrict__ rowptr, int *__restrict__ flag)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m && rowptr[r] == rowptr[r + 1]) *flag = 1;
+}
+
+template <typename T>
+__global__ void fill_zero_kernel(long long n, T *__restrict__ y)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column-banded CSR-vector (optional layout of Method_Parallel for matrices whose x does not fit
+// L2).  The non-zeros of every row are already sorted by column, so band b of row r is the
+// contiguous sub-range [band_ptr[b*m + r], band_ptr[(b+1)*m + r]) of the SAME ColIdx/Val arrays: no
+// copy of the matrix, only (K+1)*m extra row pointers.  One launch per band, in band order: every CTA of
+// a launch touches only x[b*band_cols, (b+1)*band_cols), which therefore stays L2-resident; y is
+// accumulated band by band in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int TPR, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+csr_banded_kernel(int m, int nnz, int first, const int *__restrict__ bstart, const int *__restrict__ bend,
+                  const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
+                  T *__restrict__ y)
+{
+    const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
+    const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long row_l = gt / TPR;
+    const int sl = threadIdx.x & (TPR - 1);
+    const bool valid = row_l < m;
+    const int row = valid ? (int)row_l : 0;
+    const int start = valid ? bstart[row] : 0;
+    const int end = valid ? bend[row] : 0;
+    T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
+    sum = group_sum_c<T, TPR>(sum);
+    if (valid && sl == 0) {
+        if (first) y[row] = sum; else y[row] += sum;
+    }
+}
+
+// band_ptr[b*m + r] = first position in row r whose column is >= b*band_cols (lower bound inside the
+// sorted row), b = 0..K; band K is the row end.
+__global__ void band_ptr_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
+                                const int *__restrict__ col, int *__restrict__ bptr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)m * (bands + 1)) return;
+    const int b = (int)(i / m), r = (int)(i % m);
+    int lo = rowptr[r], hi = rowptr[r + 1];
+    if (b == bands) { bptr[i] = hi; return; }
+    const long long key = (long long)b * band_cols;
+    while (lo < hi) {
+        const int mid = (int)(((long long)lo + hi) >> 1);
+        if (col[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    bptr[i] = lo;
+}
+
+// 1 in *flag when some row has a column index smaller than its predecessor (banding needs sorted rows)
+__global__ void unsorted_rows_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                     int *__restrict__ flag)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    for (int j = rowptr[r] + 1; j < rowptr[r + 1]; ++j)
+        if (col[j] < col[j - 1]) { *flag = 1; return; }
+}
+
+}  // namespace sb

@@ -1,0 +1,836 @@
+// spmv_b200.cu -- the C-ABI of libspmv_b200.so: the four drop-in entry points of include/spmv.h, the
+// exported name tables, and the extensions of include/spmv_b200.h.  Handle construction uploads (or
+// adopts) the CSR arrays once and builds the device layout of the requested SPMV_METHODS value;
+// spmv() launches the matching sm_100a kernel family.  There is no CPU compute path in this file.
+#include <cstdarg>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <map>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+#include "csr_kernels.cuh"
+#include "tile_kernels.cuh"
+#include "sell.cuh"
+#include "csr5.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------
+// error latch, launch counter, options
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[spmv_b200] %s\n", g_err);
+}
+
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line)
+{
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %s (%s) at %s:%d in `%s`", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    return false;
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+struct Options {
+    std::mutex mu;
+    std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 16}, {"block_nnz", 512},
+                                       {"tile_items", 8},   {"tpr", 0},         {"x_bands", 1}};
+    std::map<std::string, bool> user_set;
+};
+static Options &options()
+{
+    static Options o;
+    return o;
+}
+static long long opt(const char *key)
+{
+    Options &o = options();
+    std::lock_guard<std::mutex> g(o.mu);
+    auto it = o.v.find(key);
+    if (it == o.v.end()) return -1;
+    if (!o.user_set[key]) {  // environment: SPMV_B200_<KEY>
+        std::string env = "SPMV_B200_";
+        for (const char *p = key; *p; ++p) env.push_back((char)toupper(*p));
+        if (const char *e = getenv(env.c_str())) return atoll(e);
+    }
+    return it->second;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename U>
+static bool dmalloc(U **p, size_t count)
+{
+    *p = nullptr;
+    return SB_CUDA(cudaMalloc((void **)p, (count ? count : 1) * sizeof(U)));
+}
+
+static void dfree(void *p) { if (p) cudaFree(p); }
+
+static inline int blocks_for(long long threads) { return (int)((threads + kThreads - 1) / kThreads); }
+
+struct DeviceGuard {  // library code is device-agnostic: run on the handle's device, then restore
+    int prev = -1, want;
+    explicit DeviceGuard(int dev) : want(dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+
+static bool read_flag(int *d_flag, cudaStream_t s, int *out)
+{
+    SB_TRY(cudaMemcpyAsync(out, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SB_TRY(cudaStreamSynchronize(s));
+    return true;
+}
+
+template <typename V>
+static bool exclusive_scan(const V *in, V *out, int count, cudaStream_t s)
+{
+    size_t bytes = 0;
+    SB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, s));
+    void *tmp = nullptr;
+    SB_TRY(cudaMalloc(&tmp, bytes ? bytes : 1));
+    const bool ok = SB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, count, s)) &&
+                    SB_CUDA(cudaStreamSynchronize(s));
+    cudaFree(tmp);
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout builders (handle construction, a2)
+// ------------------------------------------------------------------------------------------------
+static void free_layouts(DeviceState *st)
+{
+    dfree(st->band_ptr); st->band_ptr = nullptr;
+    dfree(st->splitter); st->splitter = nullptr;
+    dfree(st->ref_splitter); st->ref_splitter = nullptr;
+    dfree(st->tile_rows); st->tile_rows = nullptr;
+    dfree(st->merge_coords); st->merge_coords = nullptr;
+    dfree(st->carry_val); st->carry_val = nullptr;
+    dfree(st->carry_row); st->carry_row = nullptr;
+    dfree(st->sell_perm); st->sell_perm = nullptr;
+    dfree(st->sell_width); st->sell_width = nullptr;
+    dfree(st->sell_full); st->sell_full = nullptr;
+    dfree(st->sell_col); st->sell_col = nullptr;
+    dfree(st->sell_slice_ptr); st->sell_slice_ptr = nullptr;
+    dfree(st->sell_val); st->sell_val = nullptr;
+    dfree(st->c5_tile_ptr); st->c5_tile_ptr = nullptr;
+    dfree(st->c5_tile_desc); st->c5_tile_desc = nullptr;
+    dfree(st->c5_off_ptr); st->c5_off_ptr = nullptr;
+    dfree(st->c5_off); st->c5_off = nullptr;
+    dfree(st->c5_col); st->c5_col = nullptr;
+    dfree(st->c5_val); st->c5_val = nullptr;
+    dfree(st->x_stage); st->x_stage = nullptr;
+    dfree(st->y_stage); st->y_stage = nullptr;
+}
+
+static void free_state(DeviceState *st)
+{
+    if (!st) return;
+    DeviceGuard g(st->device);
+    free_layouts(st);
+    if (st->owns_csr) { dfree(st->rowptr); dfree(st->col); dfree(st->val); }
+    st->magic = 0;
+    delete st;
+}
+
+static int pick_tpr(long long nnz, int m)
+{
+    const long long forced = opt("tpr");
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return (int)forced;
+    const double mean = m > 0 ? (double)nnz / m : 0.0;
+    int tpr = 1;
+    while (tpr < 32 && 4.0 * tpr < mean) tpr <<= 1;  // each lane takes 4-element chunks
+    return tpr;
+}
+
+static bool build_bands(DeviceState *st)
+{
+    long long bands = opt("x_bands");
+    if (bands <= 1 || st->m == 0 || st->nnz == 0) return true;
+    if (bands > 64) bands = 64;
+    int *flag = nullptr;
+    if (!dmalloc(&flag, 1)) return false;
+    SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
+    unsorted_rows_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(st->m, st->rowptr, st->col, flag);
+    int unsorted = 0;
+    const bool ok = read_flag(flag, st->stream, &unsorted);
+    dfree(flag);
+    if (!ok) return false;
+    if (unsorted) return true;  // rows not column-sorted: keep the plain CSR-vector kernel
+    st->x_bands = (int)bands;
+    st->band_cols = (int)(((long long)st->n + bands - 1) / bands);
+    if (!dmalloc(&st->band_ptr, (size_t)st->m * (bands + 1))) return false;
+    band_ptr_kernel<<<blocks_for((long long)st->m * (bands + 1)), kThreads, 0, st->stream>>>(
+        st->m, st->x_bands, st->band_cols, st->rowptr, st->col, st->band_ptr);
+    SB_TRY(cudaGetLastError());
+    st->kernel = SPMV_B200_KERNEL_CSR_BANDED;
+    return true;
+}
+
+// a9 on the device for `parts` partitions; *starved = some partition owns no whole row (a10)
+static bool build_splitter(DeviceState *st, int parts, int **out, int *starved)
+{
+    if (!dmalloc(out, (size_t)parts + 1)) return false;
+    splitter_kernel<<<blocks_for(parts + 1), kThreads, 0, st->stream>>>(parts, st->nnz, st->m, st->rowptr, *out);
+    SB_TRY(cudaGetLastError());
+    if (starved) {
+        int *flag = nullptr;
+        if (!dmalloc(&flag, 1)) return false;
+        SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
+        splitter_starved_kernel<<<blocks_for(parts), kThreads, 0, st->stream>>>(parts, st->m, *out, flag);
+        const bool ok = read_flag(flag, st->stream, starved);
+        dfree(flag);
+        if (!ok) return false;
+    }
+    return true;
+}
+
+static bool build_tiles(DeviceState *st, bool merge)
+{
+    int ipt = (int)opt("tile_items");
+    if (ipt != 4 && ipt != 8) ipt = 8;
+    st->tile_items = ipt;
+    const long long per_tile = (long long)kThreads * ipt;
+    const long long total = merge ? (long long)st->m + st->nnz : (long long)st->nnz;
+    st->tiles = (int)((total + per_tile - 1) / per_tile);
+    if (st->tiles < 1) st->tiles = 1;
+    if (merge) {
+        if (!dmalloc(&st->merge_coords, (size_t)st->tiles + 1)) return false;
+        merge_coords_kernel<<<blocks_for(st->tiles + 1), kThreads, 0, st->stream>>>(
+            st->tiles, (int)per_tile, st->nnz, st->m, st->rowptr, st->merge_coords);
+    } else {
+        if (!dmalloc(&st->tile_rows, (size_t)st->tiles + 1)) return false;
+        tile_rows_kernel<<<blocks_for(st->tiles + 1), kThreads, 0, st->stream>>>(
+            st->tiles, (int)per_tile, st->nnz, st->m, st->rowptr, st->tile_rows);
+    }
+    SB_TRY(cudaGetLastError());
+    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)st->tiles * st->vsize))) return false;
+    if (!dmalloc(&st->carry_row, (size_t)st->tiles)) return false;
+    st->kernel = merge ? SPMV_B200_KERNEL_MERGE_PATH : SPMV_B200_KERNEL_NNZ_SPLIT;
+    return true;
+}
+
+template <typename T>
+static bool build_sell(DeviceState *st)
+{
+    long long sigma = opt("sell_sigma");
+    if (sigma < kSellC) sigma = kSellC;
+    if (sigma > kSellMaxSigma) sigma = kSellMaxSigma;
+    sigma = (sigma / kSellC) * kSellC;
+    st->sigma = (int)sigma;
+    const int windows = st->m / st->sigma;
+    st->banner = windows * st->sigma;  // reference sell_C_Sigma_spmv.c:148-156
+    st->slices = st->banner / kSellC;
+    st->tpr = pick_tpr(st->nnz, st->m);  // for the CSR tail rows [banner, m)
+    st->kernel = SPMV_B200_KERNEL_SELL;
+    if (st->banner == 0) return true;
+    int pow2 = 1;
+    while (pow2 < st->sigma) pow2 <<= 1;
+    if (!dmalloc(&st->sell_perm, (size_t)st->banner)) return false;
+    sell_sort_kernel<<<windows, kThreads, (size_t)pow2 * sizeof(unsigned long long), st->stream>>>(
+        st->sigma, pow2, st->rowptr, st->sell_perm);
+    SB_TRY(cudaGetLastError());
+    long long *count = nullptr;
+    if (!dmalloc(&st->sell_width, (size_t)st->slices) || !dmalloc(&st->sell_full, (size_t)st->slices) ||
+        !dmalloc(&count, (size_t)st->slices + 1) || !dmalloc(&st->sell_slice_ptr, (size_t)st->slices + 1))
+        return false;
+    SB_TRY(cudaMemsetAsync(count, 0, ((size_t)st->slices + 1) * sizeof(long long), st->stream));
+    sell_width_kernel<<<blocks_for((long long)st->slices * 32), kThreads, 0, st->stream>>>(
+        st->slices, st->rowptr, st->sell_perm, st->sell_width, st->sell_full, count);
+    SB_TRY(cudaGetLastError());
+    const bool ok = exclusive_scan(count, st->sell_slice_ptr, st->slices + 1, st->stream);
+    dfree(count);
+    if (!ok) return false;
+    SB_TRY(cudaMemcpy(&st->padded, st->sell_slice_ptr + st->slices, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (!dmalloc(&st->sell_col, (size_t)st->padded)) return false;
+    if (!SB_CUDA(cudaMalloc(&st->sell_val, (size_t)(st->padded ? st->padded : 1) * sizeof(T)))) return false;
+    sell_fill_kernel<T><<<blocks_for((long long)st->slices * 32), kThreads, 0, st->stream>>>(
+        st->slices, st->rowptr, st->col, (const T *)st->val, st->sell_perm, st->sell_slice_ptr, st->sell_col,
+        (T *)st->sell_val);
+    SB_TRY(cudaGetLastError());
+    return true;
+}
+
+template <typename T>
+static bool build_csr5(DeviceState *st)
+{
+    int sigma = (int)opt("csr5_sigma");
+    if (sigma != 4 && sigma != 8 && sigma != 16) sigma = 16;
+    st->c5_sigma = sigma;
+    // anonymouslib_avx2.h:124-146 at omega = 32
+    int base = 2, by = 1;
+    while (base < kC5Omega * sigma) { base *= 2; by++; }
+    int bs = 1;
+    base = 2;
+    while (base < kC5Omega) { base *= 2; bs++; }
+    st->c5_bit_y = by;
+    st->c5_bit_ss = bs;  // by + bs + sigma <= 32 for sigma <= 16: one descriptor word per lane
+    const int tile_nnz = kC5Omega * sigma;
+    const int p = (int)(((long long)st->nnz + tile_nnz - 1) / tile_nnz);
+    st->c5_p = p;
+    st->kernel = SPMV_B200_KERNEL_CSR5;
+    st->tiles = p;
+    if (p == 0) return true;
+    uint32_t *raw = nullptr;
+    int *off_cnt = nullptr;
+    if (!dmalloc(&raw, (size_t)p + 1) || !dmalloc(&st->c5_tile_ptr, (size_t)p + 1) ||
+        !dmalloc(&st->c5_tile_desc, (size_t)p * kC5Omega) || !dmalloc(&off_cnt, (size_t)p + 1) ||
+        !dmalloc(&st->c5_off_ptr, (size_t)p + 1))
+        return false;
+    c5_tile_ptr_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, sigma, st->nnz, st->m, st->rowptr, raw);
+    c5_tile_dirty_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, st->m, st->rowptr, raw, st->c5_tile_ptr);
+    SB_TRY(cudaMemsetAsync(off_cnt, 0, ((size_t)p + 1) * sizeof(int), st->stream));
+    c5_tile_desc_kernel<<<blocks_for((long long)p * 32), kThreads, 0, st->stream>>>(
+        p, sigma, by, bs, st->rowptr, st->c5_tile_ptr, st->c5_tile_desc, off_cnt);
+    SB_TRY(cudaGetLastError());
+    bool ok = exclusive_scan(off_cnt, st->c5_off_ptr, p + 1, st->stream);
+    dfree(raw);
+    dfree(off_cnt);
+    if (!ok) return false;
+    uint32_t tail_word = 0;
+    SB_TRY(cudaMemcpy(&st->c5_num_offsets, st->c5_off_ptr + p, sizeof(int), cudaMemcpyDeviceToHost));
+    SB_TRY(cudaMemcpy(&tail_word, st->c5_tile_ptr + (p - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    st->c5_tail_start = (int)(tail_word & 0x7FFFFFFFu);  // anonymouslib_avx2.h:177
+    if (st->c5_num_offsets > 0) {
+        if (!dmalloc(&st->c5_off, (size_t)st->c5_num_offsets)) return false;
+        SB_TRY(cudaMemsetAsync(st->c5_off, 0, (size_t)st->c5_num_offsets * sizeof(int), st->stream));
+        c5_desc_offset_kernel<<<blocks_for((long long)p * 32), kThreads, 0, st->stream>>>(
+            p, sigma, by, bs, st->rowptr, st->c5_tile_ptr, st->c5_tile_desc, st->c5_off_ptr, st->c5_off);
+        SB_TRY(cudaGetLastError());
+    }
+    if (!dmalloc(&st->c5_col, (size_t)st->nnz)) return false;
+    if (!SB_CUDA(cudaMalloc(&st->c5_val, (size_t)st->nnz * sizeof(T)))) return false;
+    c5_transpose_kernel<T><<<blocks_for(st->nnz), kThreads, 0, st->stream>>>(
+        st->nnz, sigma, p, st->c5_tile_ptr, st->col, (const T *)st->val, st->c5_col, (T *)st->c5_val);
+    SB_TRY(cudaGetLastError());
+    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)p * sizeof(T)))) return false;
+    if (!dmalloc(&st->carry_row, (size_t)p)) return false;
+    return true;
+}
+
+template <typename T>
+static bool build_method(DeviceState *st, spmv_Handle *h, int method)
+{
+    switch (method) {
+    case Method_Serial:
+        st->kernel = SPMV_B200_KERNEL_CSR_REFORDER;
+        return true;
+    case Method_Parallel:
+        st->tpr = pick_tpr(st->nnz, st->m);
+        st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
+        return build_bands(st);
+    case Method_Balanced:
+    case Method_Balanced2: {
+        // mirror of the reference's demotion / promotion rule with the CALLER's nthreads (a10,
+        // parallel_balanced2_spmv.c:72-94) for clients that read handle->spmvMethod
+        st->ref_T = (int)(h->nthreads ? (h->nthreads > (1u << 24) ? (1u << 24) : h->nthreads) : 1);
+        int ref_starved = 0;
+        if (!build_splitter(st, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
+        h->spmvMethod = ref_starved ? Method_Balanced2 : Method_Balanced;
+        // the GPU geometry: row blocks of ~block_nnz non-zeros, one warp each
+        long long block_nnz = opt("block_nnz");
+        if (block_nnz < 32) block_nnz = 32;
+        st->parts = (int)(((long long)st->nnz + block_nnz - 1) / block_nnz);
+        if (st->parts < 1) st->parts = 1;
+        int starved = 0;
+        if (!build_splitter(st, st->parts, &st->splitter, &starved)) return false;
+        // Balanced2 was asked for, or a row is long enough to starve a row block: merge-path
+        if (method == Method_Balanced2 || starved) return build_tiles(st, /*merge=*/true);
+        st->kernel = SPMV_B200_KERNEL_ROW_BLOCKS;
+        return true;
+    }
+    case Method_Balanced_Yid:
+        return build_tiles(st, /*merge=*/false);
+    case Method_SellCSigma:
+        return build_sell<T>(st);
+    case Method_CSR5SPMV:
+        return build_csr5<T>(st);
+    default:
+        st->kernel = SPMV_B200_KERNEL_CSR_REFORDER;
+        return true;
+    }
+}
+
+static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowPtr, int *ColIdx, void *Val,
+                        int method)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libspmv_b200 has no CPU fallback");
+        return false;
+    }
+    SB_TRY(cudaGetDevice(&st->device));
+    if (m < 0 || n < 0 || (m > 0 && (!RowPtr))) { set_error("invalid arguments (m=%d n=%d RowPtr=%p)", m, n, (void *)RowPtr); return false; }
+    st->m = m;
+    st->n = n;
+    st->vsize = (h->data_size == sizeof(double)) ? 8 : 4;  // reference serial_spmv.c:48-54
+    st->requested = method;
+
+    const bool dev_csr = is_device_ptr(RowPtr);
+    int ends[2] = {0, 0};
+    if (dev_csr) {
+        if (m > 0) {
+            SB_TRY(cudaMemcpy(&ends[0], RowPtr, sizeof(int), cudaMemcpyDeviceToHost));
+            SB_TRY(cudaMemcpy(&ends[1], RowPtr + m, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+    } else if (m > 0) {
+        ends[0] = RowPtr[0];
+        ends[1] = RowPtr[m];
+    }
+    if (ends[0] != 0 || ends[1] < 0) { set_error("RowPtr[0] must be 0 and RowPtr[m] >= 0 (got %d, %d)", ends[0], ends[1]); return false; }
+    if ((long long)ends[1] > 2147483647LL - 8192) { set_error("nnz too large for 32-bit tiles"); return false; }
+    st->nnz = ends[1];
+    if (st->nnz > 0 && (!ColIdx || !Val)) { set_error("ColIdx / Matrix_Val are NULL"); return false; }
+
+    if (dev_csr) {
+        // device-resident CSR: adopted in place (borrowed, like the reference borrows host arrays)
+        if (st->nnz > 0 && (!is_device_ptr(ColIdx) || !is_device_ptr(Val))) { set_error("RowPtr is a device pointer but ColIdx / Matrix_Val are not"); return false; }
+        st->rowptr = RowPtr;
+        st->col = ColIdx;
+        st->val = Val;
+        st->owns_csr = false;
+    } else {
+        // upload once; 32 bytes of slack so that aligned chunk loads never leave the allocation
+        st->owns_csr = true;
+        if (!dmalloc(&st->rowptr, (size_t)m + 1 + 8) || !dmalloc(&st->col, (size_t)st->nnz + 8)) return false;
+        if (!SB_CUDA(cudaMalloc(&st->val, ((size_t)st->nnz + 8) * st->vsize))) return false;
+        if (m > 0) SB_TRY(cudaMemcpy(st->rowptr, RowPtr, ((size_t)m + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        else SB_TRY(cudaMemset(st->rowptr, 0, sizeof(int)));
+        if (st->nnz > 0) {
+            SB_TRY(cudaMemcpy(st->col, ColIdx, (size_t)st->nnz * sizeof(int), cudaMemcpyHostToDevice));
+            SB_TRY(cudaMemcpy(st->val, Val, (size_t)st->nnz * st->vsize, cudaMemcpyHostToDevice));
+        }
+    }
+    st->vec_ok = (((uintptr_t)st->col | (uintptr_t)st->val) & 31u) == 0;
+
+    if (m > 0) {
+        int *flag = nullptr;
+        if (!dmalloc(&flag, 1)) return false;
+        SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
+        empty_rows_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->rowptr, flag);
+        int e = 0;
+        const bool ok = read_flag(flag, st->stream, &e);
+        dfree(flag);
+        if (!ok) return false;
+        st->has_empty_rows = e != 0;
+    }
+    if (m == 0 || st->nnz == 0) {  // nothing to lay out: spmv() only has zeros to write
+        st->kernel = SPMV_B200_KERNEL_NONE;
+        return true;
+    }
+    const bool ok = st->vsize == 8 ? build_method<double>(st, h, method) : build_method<float>(st, h, method);
+    if (!ok) return false;
+    SB_TRY(cudaStreamSynchronize(st->stream));
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch dispatch (a3: the reference's spmv_functions[] table, common.c:85-94)
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+static void launch_vector(DeviceState *st, int tpr, const T *x, T *y)
+{
+    const int m = st->m;
+    const int grid = blocks_for((long long)m * tpr);
+#define SB_CASE(N) case N: csr_vector_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->rowptr, st->col, (const T *)st->val, x, y); break;
+    switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
+#undef SB_CASE
+    count_launch();
+}
+
+template <typename T, bool VEC>
+static void launch_banded(DeviceState *st, const T *x, T *y)
+{
+    const int m = st->m;
+    // lanes per row sized for a band's share of the row
+    int tpr = 1;
+    const double mean = (double)st->nnz / m / st->x_bands;
+    while (tpr < 32 && 4.0 * tpr < mean) tpr <<= 1;
+    const int grid = blocks_for((long long)m * tpr);
+    for (int b = 0; b < st->x_bands; ++b) {
+        const int *bs = st->band_ptr + (size_t)b * m, *be = st->band_ptr + (size_t)(b + 1) * m;
+#define SB_CASE(N) case N: csr_banded_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, b == 0, bs, be, st->col, (const T *)st->val, x, y); break;
+        switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
+#undef SB_CASE
+    }
+    count_launch(st->x_bands);
+}
+
+// CSR-vector over rows [row0, m) only (the CSR tail of SELL)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+csr_tail_kernel(int row0, int m, const int *__restrict__ rowptr, const int *__restrict__ col,
+                const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y)
+{
+    const uint64_t pl = policy_evict_last();
+    const long long w = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row0 + w >= m) return;
+    const int row = (int)(row0 + w);
+    T sum = 0;
+    for (int j = rowptr[row] + lane; j < rowptr[row + 1]; j += 32) sum = fma_t(val[j], ldg_x(x + col[j], pl), sum);
+    sum = group_sum_c<T, 32>(sum);
+    if (lane == 0) y[row] = sum;
+}
+
+template <typename T>
+static bool launch(DeviceState *st, const T *x, T *y)
+{
+    cudaStream_t s = st->stream;
+    const int m = st->m;
+    if (m == 0) return true;
+    if (st->kernel == SPMV_B200_KERNEL_NONE) {  // nnz == 0: y = 0
+        fill_zero_kernel<T><<<blocks_for(m), kThreads, 0, s>>>(m, y);
+        count_launch();
+        return SB_CUDA(cudaGetLastError());
+    }
+    const T *val = (const T *)st->val;
+    switch (st->kernel) {
+    case SPMV_B200_KERNEL_CSR_REFORDER: {
+        constexpr int L = sizeof(T) == 8 ? 4 : 8;
+        csr_reforder_kernel<T><<<blocks_for((long long)m * L), kThreads, 0, s>>>(m, st->rowptr, st->col, val, x, y);
+        count_launch();
+        break;
+    }
+    case SPMV_B200_KERNEL_CSR_VECTOR:
+        if (st->vec_ok) launch_vector<T, true>(st, st->tpr, x, y); else launch_vector<T, false>(st, st->tpr, x, y);
+        break;
+    case SPMV_B200_KERNEL_CSR_BANDED:
+        if (st->vec_ok) launch_banded<T, true>(st, x, y); else launch_banded<T, false>(st, x, y);
+        break;
+    case SPMV_B200_KERNEL_ROW_BLOCKS: {
+        const int grid = blocks_for((long long)st->parts * 32);
+        if (st->vec_ok) row_block_kernel<T, true><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->rowptr, st->col, val, x, y);
+        else row_block_kernel<T, false><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->rowptr, st->col, val, x, y);
+        count_launch();
+        break;
+    }
+    case SPMV_B200_KERNEL_MERGE_PATH: {
+        if (st->tile_items == 4)
+            merge_path_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+        else
+            merge_path_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+        carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
+        count_launch(2);
+        break;
+    }
+    case SPMV_B200_KERNEL_NNZ_SPLIT: {
+        if (st->tile_items == 4)
+            nnz_split_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+        else
+            nnz_split_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+        carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
+        count_launch(2);
+        break;
+    }
+    case SPMV_B200_KERNEL_SELL: {
+        if (st->slices > 0) {
+            sell_kernel<T><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
+                st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y);
+            count_launch();
+        }
+        if (st->banner < m) {
+            csr_tail_kernel<T><<<blocks_for((long long)(m - st->banner) * 32), kThreads, 0, s>>>(st->banner, m, st->rowptr, st->col, val, x, y);
+            count_launch();
+        }
+        break;
+    }
+    case SPMV_B200_KERNEL_CSR5: {
+        const int p = st->c5_p;
+        if (st->has_empty_rows) {
+            fill_zero_kernel<T><<<blocks_for(m), kThreads, 0, s>>>(m, y);
+            count_launch();
+        }
+        const T *tval = (const T *)st->c5_val;
+        if (p > 1) {
+            const int grid = blocks_for((long long)(p - 1) * 32);
+#define SB_C5(SG) csr5_kernel<T, SG><<<grid, kThreads, 0, s>>>(p, st->c5_bit_y, st->c5_bit_ss, st->c5_tile_ptr, st->c5_tile_desc, st->c5_off_ptr, st->c5_off, st->c5_col, tval, x, y, (T *)st->carry_val, st->carry_row)
+            if (st->c5_sigma == 4) SB_C5(4); else if (st->c5_sigma == 8) SB_C5(8); else SB_C5(16);
+#undef SB_C5
+            count_launch();
+        }
+        const int tail_nz0 = (p - 1) * kC5Omega * st->c5_sigma;
+        csr5_tail_kernel<T><<<blocks_for((long long)(m - st->c5_tail_start) * 32), kThreads, 0, s>>>(
+            m, st->c5_tail_start, tail_nz0, p - 1, st->rowptr, st->c5_col, tval, x, y, (T *)st->carry_val, st->carry_row);
+        carry_fixup_kernel<T><<<blocks_for(p), kThreads, 0, s>>>(p, st->carry_row, (const T *)st->carry_val, y);
+        count_launch(2);
+        break;
+    }
+    default:
+        set_error("handle has no kernel (%d)", st->kernel);
+        return false;
+    }
+    return SB_CUDA(cudaGetLastError());
+}
+
+static DeviceState *state_of(const spmv_Handle *h)
+{
+    if (!h || !h->extraHandle) return nullptr;
+    DeviceState *st = (DeviceState *)h->extraHandle;
+    return st->magic == 0x5b200a11u ? st : nullptr;
+}
+
+static void handle_init(spmv_Handle *h)  // reference gemv_Handle_init, common.c:18-29
+{
+    h->spmvMethod = Method_Serial;
+    h->nthreads = 0;
+    h->extraHandle = nullptr;
+    h->RowPtr = nullptr;
+    h->ColIdx = nullptr;
+    h->Matrix_Val = nullptr;
+    h->Y_temp = nullptr;
+    h->index = nullptr;
+    h->Level_3_opt_used = 0;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// ================================================================================================
+// exported data (reference common.c:306-339; same strings, same order)
+// ================================================================================================
+extern "C" {
+
+const char *funcNames[] = {
+    "Method_Serial_VECTOR_NONE", "Method_Serial_VECTOR_AVX2", "Method_Serial_VECTOR_AVX512",
+    "Method_Parallel_VECTOR_NONE", "Method_Parallel_VECTOR_AVX2", "Method_Parallel_VECTOR_AVX512",
+    "Method_Balanced_VECTOR_NONE", "Method_Balanced_VECTOR_AVX2", "Method_Balanced_VECTOR_AVX512",
+    "Method_Balanced2_VECTOR_NONE", "Method_Balanced2_VECTOR_AVX2", "Method_Balanced2_VECTOR_AVX512",
+    "Method_SellCSigma_VECTOR_NONE", "Method_SellCSigma_VECTOR_AVX2", "Method_SellCSigma_VECTOR_AVX512",
+    "Method_Csr5Spmv_VECTOR_NONE", "Method_Csr5Spmv_VECTOR_AVX2", "Method_Csr5Spmv_VECTOR_AVX512"};
+const char *Methods_names[] = {"Method_Serial", "Method_Parallel", "Method_Balanced", "Method_Balanced2",
+                               "Method_BalancedYid", "Method_SellCSigma", "Method_Csr5Spmv"};
+const char *Vectorized_names[] = {"VECTOR_NONE", "VECTOR_AVX2", "VECTOR_AVX512"};
+
+// ================================================================================================
+// the four drop-in entry points
+// ================================================================================================
+void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASIC_INT_TYPE n,
+                                   BASIC_INT_TYPE *RowPtr, BASIC_INT_TYPE *ColIdx, void *Matrix_Val,
+                                   BASIC_SIZE_TYPE nthreads, SPMV_METHODS Function, BASIC_SIZE_TYPE size,
+                                   VECTORIZED_WAY vectorizedWay, const char *MtxToken)
+{
+    (void)MtxToken;  // only keys the reference's compiled-out METIS cache (common.c:152-154)
+    if (!Handle) return;
+    spmv_Handle *h = (spmv_Handle *)malloc(sizeof(spmv_Handle));  // freed by spmv_destory_handle
+    *Handle = h;
+    if (!h) return;
+    handle_init(h);
+    int method = (int)Function;
+    if (method < (int)Method_Serial || method >= (int)Method_Total_Size) method = Method_Serial;  // common.c:136
+    h->nthreads = nthreads;  // handle_init_common_parameters, common.c:74-83
+    h->vectorizedWay = vectorizedWay;
+    h->data_size = size;
+    h->spmvMethod = (SPMV_METHODS)method;
+    h->RowPtr = RowPtr;  // borrowed, never written (common.c:157-159)
+    h->ColIdx = ColIdx;
+    h->Matrix_Val = Matrix_Val;
+    if (method == Method_CSR5SPMV && size != sizeof(double)) {
+        // the reference silently runs SELL for fp32 "CSR5" (common.c:177-180); we run a real fp32 CSR5
+        // but keep what a client would read from the handle
+        h->spmvMethod = Method_CSR5SPMV;
+    }
+    DeviceState *st = new DeviceState();
+    h->extraHandle = st;
+    st->ok = build_state(st, h, m, n, RowPtr, ColIdx, Matrix_Val, method);
+}
+
+void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *RowPtr,
+          const BASIC_INT_TYPE *ColIdx, const void *Matrix_Val, const void *Vector_Val_X, void *Vector_Val_Y)
+{
+    (void)m; (void)RowPtr; (void)ColIdx; (void)Matrix_Val;  // the handle owns the device copies
+    DeviceState *st = state_of(handle);  // NULL handle: silent return (common.c:285)
+    if (!st || !st->ok || !Vector_Val_Y || (!Vector_Val_X && st->n > 0)) return;
+    DeviceGuard guard(st->device);
+    const bool x_dev = is_device_ptr(Vector_Val_X), y_dev = is_device_ptr(Vector_Val_Y);
+    const void *xd = Vector_Val_X;
+    void *yd = Vector_Val_Y;
+    const size_t xb = (size_t)st->n * st->vsize, yb = (size_t)st->m * st->vsize;
+    if (!x_dev) {
+        if (!st->x_stage && !SB_CUDA(cudaMalloc(&st->x_stage, xb ? xb : 1))) return;
+        if (xb && !SB_CUDA(cudaMemcpyAsync(st->x_stage, Vector_Val_X, xb, cudaMemcpyHostToDevice, st->stream))) return;
+        xd = st->x_stage;
+    }
+    if (!y_dev) {
+        if (!st->y_stage && !SB_CUDA(cudaMalloc(&st->y_stage, yb ? yb : 1))) return;
+        yd = st->y_stage;
+    }
+    const bool ok = st->vsize == 8 ? launch<double>(st, (const double *)xd, (double *)yd)
+                                   : launch<float>(st, (const float *)xd, (float *)yd);
+    if (!ok) return;
+    if (!y_dev) {
+        if (yb && !SB_CUDA(cudaMemcpyAsync(Vector_Val_Y, yd, yb, cudaMemcpyDeviceToHost, st->stream))) return;
+        SB_CUDA(cudaStreamSynchronize(st->stream));  // host y is complete on return, as in the reference
+    }
+}
+
+void spmv_clear_handle(spmv_Handle_t this_handle)  // reference gemv_Handle_clear, common.c:31-52,69-71
+{
+    if (!this_handle) return;
+    free_state(state_of(this_handle));
+    handle_init(this_handle);
+}
+
+void spmv_destory_handle(spmv_Handle_t this_handle)  // reference common.c:54-61
+{
+    if (!this_handle) return;
+    spmv_clear_handle(this_handle);
+    free(this_handle);
+}
+
+// ================================================================================================
+// extensions (include/spmv_b200.h)
+// ================================================================================================
+int spmv_b200_version(void) { return SPMV_B200_VERSION; }
+const char *spmv_b200_last_error(void) { return g_err; }
+void spmv_b200_clear_error(void) { g_err[0] = 0; }
+unsigned long long spmv_b200_launch_count(void) { return g_launches.load(); }
+
+void spmv_b200_set_stream(spmv_Handle_t handle, void *cuda_stream)
+{
+    if (DeviceState *st = state_of(handle)) st->stream = (cudaStream_t)cuda_stream;
+}
+
+void spmv_b200_sync(spmv_Handle_t handle)
+{
+    if (DeviceState *st = state_of(handle)) {
+        DeviceGuard g(st->device);
+        SB_CUDA(cudaStreamSynchronize(st->stream));
+    }
+}
+
+int spmv_b200_set_option(const char *key, long long value)
+{
+    Options &o = options();
+    std::lock_guard<std::mutex> g(o.mu);
+    auto it = o.v.find(key ? key : "");
+    if (it == o.v.end()) return -1;
+    it->second = value;
+    o.user_set[key] = true;
+    return 0;
+}
+
+long long spmv_b200_get_option(const char *key) { return key ? opt(key) : -1; }
+
+long long spmv_b200_info(spmv_Handle_t handle, const char *key)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || !key) return -1;
+    const std::string k(key);
+    if (k == "kernel") return st->kernel;
+    if (k == "requested") return st->requested;
+    if (k == "ok") return st->ok;
+    if (k == "m") return st->m;
+    if (k == "n") return st->n;
+    if (k == "nnz") return st->nnz;
+    if (k == "tpr") return st->tpr;
+    if (k == "parts") return st->parts;
+    if (k == "ref_parts") return st->ref_T;
+    if (k == "tiles") return st->tiles;
+    if (k == "tile_items") return st->tile_items;
+    if (k == "sigma") return st->sigma;
+    if (k == "banner") return st->banner;
+    if (k == "slices") return st->slices;
+    if (k == "padded_nnz") return st->padded;
+    if (k == "csr5_p") return st->c5_p;
+    if (k == "csr5_sigma") return st->c5_sigma;
+    if (k == "csr5_bit_y_offset") return st->c5_bit_y;
+    if (k == "csr5_bit_scansum_offset") return st->c5_bit_ss;
+    if (k == "csr5_num_offsets") return st->c5_num_offsets;
+    if (k == "csr5_tail_start") return st->c5_tail_start;
+    if (k == "device") return st->device;
+    if (k == "has_empty_rows") return st->has_empty_rows;
+    if (k == "x_bands") return st->x_bands;
+    if (k == "owns_csr") return st->owns_csr;
+    if (k == "vec_ok") return st->vec_ok;
+    return -1;
+}
+
+long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || !name) return -1;
+    const std::string k(name);
+    const void *src = nullptr;
+    size_t bytes = 0;
+    if (k == "splitter") { src = st->splitter; bytes = ((size_t)st->parts + 1) * 4; }
+    else if (k == "ref_splitter") { src = st->ref_splitter; bytes = ((size_t)st->ref_T + 1) * 4; }
+    else if (k == "tile_rows") { src = st->tile_rows; bytes = ((size_t)st->tiles + 1) * 4; }
+    else if (k == "merge_coords") { src = st->merge_coords; bytes = ((size_t)st->tiles + 1) * 8; }
+    else if (k == "sell_perm") { src = st->sell_perm; bytes = (size_t)st->banner * 4; }
+    else if (k == "sell_width") { src = st->sell_width; bytes = (size_t)st->slices * 4; }
+    else if (k == "sell_full") { src = st->sell_full; bytes = (size_t)st->slices * 4; }
+    else if (k == "sell_slice_ptr") { src = st->sell_slice_ptr; bytes = ((size_t)st->slices + 1) * 8; }
+    else if (k == "sell_col") { src = st->sell_col; bytes = (size_t)st->padded * 4; }
+    else if (k == "sell_val") { src = st->sell_val; bytes = (size_t)st->padded * st->vsize; }
+    else if (k == "csr5_tile_ptr") { src = st->c5_tile_ptr; bytes = ((size_t)st->c5_p + 1) * 4; }
+    else if (k == "csr5_tile_desc") { src = st->c5_tile_desc; bytes = (size_t)st->c5_p * kC5Omega * 4; }
+    else if (k == "csr5_offset_ptr") { src = st->c5_off_ptr; bytes = ((size_t)st->c5_p + 1) * 4; }
+    else if (k == "csr5_offsets") { src = st->c5_off; bytes = (size_t)st->c5_num_offsets * 4; }
+    else if (k == "csr5_col") { src = st->c5_col; bytes = (size_t)st->nnz * 4; }
+    else if (k == "csr5_val") { src = st->c5_val; bytes = (size_t)st->nnz * st->vsize; }
+    else if (k == "band_ptr") { src = st->band_ptr; bytes = st->band_ptr ? (size_t)st->m * (st->x_bands + 1) * 4 : 0; }
+    else return -1;
+    if (!src) bytes = 0;
+    if (!dst || bytes == 0) return (long long)bytes;
+    if (dst_bytes < bytes) { set_error("structure %s needs %zu bytes, got %zu", name, bytes, dst_bytes); return -1; }
+    DeviceGuard g(st->device);
+    if (!SB_CUDA(cudaStreamSynchronize(st->stream))) return -1;
+    if (!SB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost))) return -1;
+    return (long long)bytes;
+}
+
+int spmv_b200_partition_rows(const int *RowPtr, int m, int parts, int *splitter_out)
+{
+    if (!RowPtr || !splitter_out || m < 0 || parts < 1) return -1;
+    const int nnz = RowPtr[m] - RowPtr[0];
+    const long long stride = ((long long)nnz + parts - 1) / parts;
+    for (int g = 0; g <= parts; ++g) {
+        long long b = (long long)g * stride;
+        if (b > nnz) b = nnz;
+        splitter_out[g] = right_boundary(RowPtr, (int)b, m + 1) - 1;
+    }
+    return 0;
+}
+
+void *spmv_b200_malloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (!SB_CUDA(cudaMalloc(&p, bytes ? bytes : 1))) return nullptr;
+    return p;
+}
+
+void spmv_b200_free(void *device_ptr) { dfree(device_ptr); }
+
+int spmv_b200_memcpy(void *dst, const void *src, size_t bytes, int kind)
+{
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    return SB_CUDA(cudaMemcpy(dst, src, bytes, k)) ? 0 : -1;
+}
+
+}  // extern "C"

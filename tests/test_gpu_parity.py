@@ -1,0 +1,155 @@
+"""Parity of the CUDA path against the reference's Method_Serial, through the C-ABI.  Needs a B200.
+
+The checker is oracle/_ref/libmv_l2.so (the unmodified reference, when its built .so travelled with the
+repo) or the bit-identical port oracle/liboracle.so.  Bars (BASELINE.json north_star):
+  * |y - y_ref| <= 8*eps*sum_j|a_ij x_j| per row for every SPMV_METHODS value, fp64 and fp32;
+  * Method_Serial on the GPU is BITWISE equal to the reference's Method_Serial;
+  * repeated runs are bitwise reproducible.
+On rows longer than LONG_ROW the reference's own 4/8-lane chains carry ~sqrt(len)*eps of rounding error,
+so there the bound is asserted against the extended-precision sum (oracle_spmv_exact) instead.
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+from cases import all_cases
+from spmv_b200 import api, matrices as M
+
+pytestmark = pytest.mark.gpu
+
+LONG_ROW = 1024
+METHODS = list(range(7))
+CASES = all_cases()
+
+
+@pytest.fixture(scope="module")
+def serial_ref(port):
+    from oracle import oracle as O
+    if O.have_reference():
+        R = O.Reference()
+        return lambda a, x: R.serial(a.rowptr, a.col, a.val, x)
+    return lambda a, x: port.spmv_serial(a.rowptr, a.col, a.val, x)
+
+
+def check_y(port, serial_ref, a, x, y, method, tag=""):
+    eps = np.finfo(a.val.dtype).eps
+    y_ref = serial_ref(a, x)
+    S = port.row_abs_sum(a.rowptr, a.col, a.val, x)
+    tol = 8 * eps * S
+    lens = np.diff(a.rowptr)
+    err = np.abs(y.astype(np.float64) - y_ref.astype(np.float64))
+    short = lens <= LONG_ROW
+    bad = np.nonzero(short & ~(err <= tol))[0]
+    assert len(bad) == 0, f"{tag}: {len(bad)} rows off vs Method_Serial; first row {bad[0]} len {lens[bad[0]]} " \
+                          f"y={y[bad[0]]!r} ref={y_ref[bad[0]]!r} tol={tol[bad[0]]:.3e}"
+    if method != api.Method_Serial:
+        y_ex = port.spmv_exact(a.rowptr, a.col, a.val, x)
+        err2 = np.abs(y.astype(np.float64) - y_ex.astype(np.float64))
+        # half an ulp of the result itself is unavoidable when rounding the exact sum to the value type
+        bad = np.nonzero(~(err2 <= tol + 0.5 * eps * np.abs(y_ex)))[0]
+        assert len(bad) == 0, f"{tag}: {len(bad)} rows off vs exact sum; first row {bad[0]} len {lens[bad[0]]} " \
+                              f"y={y[bad[0]]!r} exact={y_ex[bad[0]]!r} tol={tol[bad[0]]:.3e}"
+    if method == api.Method_Serial:
+        assert bits_equal(y, y_ref), f"{tag}: Method_Serial is not bit-identical to the reference"
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_all_methods_match_reference_serial(libpath, port, serial_ref, name, dt):
+    a = CASES[name]().astype(dt)
+    x = M.make_x(a.n, 4321, dt)
+    for method in METHODS:
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method, nthreads=8)
+        y = np.full(a.m, np.nan, dtype=dt)
+        h.spmv(x, y)
+        tag = f"{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
+        assert not np.isnan(y).any(), tag + ": rows left unwritten"
+        check_y(port, serial_ref, a, x, y, method, tag)
+        y2 = np.full(a.m, np.nan, dtype=dt)
+        h.spmv(x, y2)
+        assert bits_equal(y, y2), tag + ": not reproducible run to run"
+        h.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+def test_signed_data_with_cancellation(libpath, port, serial_ref, dt):
+    """Mixed-sign values and x: the bound is relative to sum|a x|, not to |y|."""
+    rng = np.random.default_rng(17)
+    for name in ("skew", "uni32", "lap48", "hub"):
+        a = CASES[name]().astype(dt)
+        a.val[:] = rng.standard_normal(a.nnz).astype(dt) * (10.0 ** rng.integers(-3, 4, a.nnz)).astype(dt)
+        x = rng.standard_normal(a.n).astype(dt)
+        for method in METHODS:
+            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method, nthreads=4)
+            y = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y)
+            check_y(port, serial_ref, a, x, y, method, f"signed/{name}/{api.METHOD_NAMES[method]}")
+            h.destroy()
+
+
+def test_device_pointers_and_adopted_device_csr(libpath, port, serial_ref):
+    """x / y / CSR already resident in HBM (torch tensors): same bits as the staged host path."""
+    import torch
+    a = CASES["skew"]()
+    x = M.make_x(a.n, 9, np.float64)
+    dev = torch.device("cuda:0")
+    rp, ci, va = (torch.from_numpy(t).to(dev) for t in (a.rowptr, a.col, a.val))
+    xd = torch.from_numpy(x).to(dev)
+    for method in METHODS:
+        h_host = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+        y_host = np.empty(a.m)
+        h_host.spmv(x, y_host)
+        h_dev = api.Handle(a.m, a.n, rp, ci, va, method)
+        assert h_dev.info("owns_csr") == 0 and h_host.info("owns_csr") == 1
+        yd = torch.full((a.m,), float("nan"), dtype=torch.float64, device=dev)
+        h_dev.spmv(xd, yd)
+        h_dev.sync()
+        assert bits_equal(yd.cpu().numpy(), y_host), api.METHOD_NAMES[method]
+        # mixed: device x, host y
+        y_mixed = np.empty(a.m)
+        h_dev.spmv(xd, y_mixed)
+        assert bits_equal(y_mixed, y_host)
+        h_host.destroy()
+        h_dev.destroy()
+    # the caller's arrays are never modified (the reference's CSR5 transposes them in place)
+    assert np.array_equal(ci.cpu().numpy(), a.col) and np.array_equal(va.cpu().numpy(), a.val)
+
+
+def test_handle_semantics_follow_the_reference(libpath):
+    a = CASES["lap48"]()
+    x = M.make_x(a.n, 1, np.float64)
+    # out-of-range method -> Method_Serial (common.c:136), Method_Numa included
+    for bad in (-1, 7, 8, 99):
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, bad)
+        assert h.struct.spmvMethod == api.Method_Serial and h.kernel == "csr_reforder"
+        h.destroy()
+    h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma, nthreads=12, vectorizedWay=api.VECTOR_AVX512)
+    s = h.struct
+    assert (s.nthreads, s.vectorizedWay, s.data_size, s.Level_3_opt_used) == (12, api.VECTOR_AVX512, 8, 0)
+    assert s.RowPtr == a.rowptr.ctypes.data and s.ColIdx == a.col.ctypes.data and s.Matrix_Val == a.val.ctypes.data
+    assert not s.index and not s.Y_temp
+    # clear: handle reusable/inert afterwards, spmv is a no-op
+    api.spmv_clear_handle(h.h)
+    assert h.struct.spmvMethod == api.Method_Serial and not h.struct.extraHandle
+    y = np.full(a.m, 7.0)
+    h.spmv(x, y)
+    assert (y == 7.0).all()
+    h.destroy()
+    # size other than sizeof(double) means float (serial_spmv.c:48-54)
+    a32 = a.astype(np.float32)
+    h = api.Handle(a.m, a.n, a32.rowptr, a32.col, a32.val, api.Method_Parallel, size=4)
+    assert h.struct.data_size == 4
+    h.destroy()
+
+
+def test_balanced_demotion_rule_mirrors_reference(libpath, port):
+    """handle->spmvMethod after create follows parallel_balanced2_spmv.c:72-94 with the caller's nthreads."""
+    for name in ("lap48", "skew", "longrow0", "hub", "uni32"):
+        a = CASES[name]()
+        for T in (1, 4, 64):
+            use_bal, _ = port.balanced2_yid(port.splitter(a.rowptr, T), a.m)
+            for req in (api.Method_Balanced, api.Method_Balanced2):
+                h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, req, nthreads=T)
+                assert h.struct.spmvMethod == (api.Method_Balanced if use_bal else api.Method_Balanced2), (name, T, req)
+                assert np.array_equal(h.structure("ref_splitter", np.int32), port.splitter(a.rowptr, T))
+                h.destroy()
