@@ -157,15 +157,23 @@ def cpu_time_reference(steps: int, warmup: int, small: bool, budget_s: float = 2
         R = O.Reference()
         T = R.max_threads()
         best = None
+        # spin the OpenMP team up first: the first ~second of parallel regions in a fresh process runs
+        # 100x slow on these hosts (thread creation + cgroup ramp-up) and would bias the method choice
+        h = R.create(A.m, A.n, A.rowptr, A.col, A.val, T, 1)
+        y = np.zeros(A.m)
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            R.spmv(h, x, y)
+        h.destroy()
         for method in (1, 2, 3, 4, 5, 6):
             h = R.create(A.m, A.n, A.rowptr, A.col, A.val, T, method)
             y = np.zeros(A.m)
             R.spmv(h, x, y)
-            t0 = time.perf_counter()
-            reps = 3
+            reps, dt = 3, 1e9
             for _ in range(reps):
+                t0 = time.perf_counter()
                 R.spmv(h, x, y)
-            dt = (time.perf_counter() - t0) / reps
+                dt = min(dt, time.perf_counter() - t0)
             log(f"  cpu reference {O.Reference.__name__} method {method}: {dt * 1e3:.2f} ms")
             if best is None or dt < best[1]:
                 if best:
