@@ -41,7 +41,12 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "block_nnz"       nnz per row block of Method_Balanced (default 512)
  *   "tile_items"      items per thread of the merge-path / equal-nnz tiles (4..16; default 8)
  *   "tpr"             force threads-per-row of Method_Parallel (power of two <= 32; 0 = from mean)
- *   "x_bands"         column bands for x locality in Method_Parallel (0 = automatic, 1 = off)
+ *   "x_bands"         column bands of the band-major layout that keeps the gathered slice of x inside L2
+ *                     (0 = automatic from n and the L2 size, 1 = off, 2..64 forced); every method except
+ *                     Method_Serial can run on the band-major copy
+ *   "l2_persist"      bytes of L2 set aside for persisting lines at create (0 = leave, -1 = device max)
+ *   "l2_fetch"        cudaLimitMaxL2FetchGranularity at create (0 = leave; 32 / 64 / 128)
+ *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
  * Returns 0, or -1 for an unknown key. */
 SPMV_B200_API int spmv_b200_set_option(const char *key, long long value);
 SPMV_B200_API long long spmv_b200_get_option(const char *key);
@@ -50,7 +55,7 @@ SPMV_B200_API long long spmv_b200_get_option(const char *key);
  * spmv_b200_info: scalar facts about a handle.  Keys: "kernel" (internal kernel family, see
  * SPMV_B200_KERNEL_*), "requested", "m", "n", "nnz", "tpr", "parts", "tiles", "sigma", "banner",
  * "slices", "padded_nnz", "csr5_p", "csr5_sigma", "csr5_num_offsets", "csr5_tail_start", "device",
- * "has_empty_rows", "x_bands", "owns_csr".  Returns -1 for an unknown key / NULL handle.
+ * "has_empty_rows", "x_bands", "band_cols", "active_rows", "owns_csr", "dev_l2_bytes".  Returns -1 for an unknown key / NULL handle.
  *
  * spmv_b200_structure: copy a device layout array to HOST memory.  Returns its size in bytes (call
  * with dst = NULL to size it), or -1.  Names: "splitter" (int[parts+1], a9), "ref_splitter"
@@ -58,7 +63,7 @@ SPMV_B200_API long long spmv_b200_get_option(const char *key);
  * (int[2*(tiles+1)]), "sell_perm" (int[banner], a13), "sell_width" (int[slices]), "sell_slice_ptr"
  * (long long[slices+1]), "sell_col" (int[padded]), "sell_val", "csr5_tile_ptr" (unsigned[p+1], a16),
  * "csr5_tile_desc" (unsigned[p*32], a17), "csr5_offset_ptr" (int[p+1]), "csr5_offsets" (int[num]),
- * "csr5_col" (int[nnz], a18), "csr5_val". */
+ * "csr5_col" (int[nnz], a18), "csr5_val", "band_rowptr" (int[x_bands*m+1]), "band_col" (int[nnz]). */
 enum {
     SPMV_B200_KERNEL_NONE = 0,
     SPMV_B200_KERNEL_CSR_REFORDER = 1, /* Method_Serial   */
@@ -67,8 +72,7 @@ enum {
     SPMV_B200_KERNEL_MERGE_PATH = 4,   /* Method_Balanced2 */
     SPMV_B200_KERNEL_NNZ_SPLIT = 5,    /* Method_Balanced_Yid */
     SPMV_B200_KERNEL_SELL = 6,         /* Method_SellCSigma */
-    SPMV_B200_KERNEL_CSR5 = 7,         /* Method_CSR5SPMV */
-    SPMV_B200_KERNEL_CSR_BANDED = 8    /* Method_Parallel with column bands */
+    SPMV_B200_KERNEL_CSR5 = 7          /* Method_CSR5SPMV */
 };
 SPMV_B200_API long long spmv_b200_info(spmv_Handle_t handle, const char *key);
 SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes);

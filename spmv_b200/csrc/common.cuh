@@ -42,6 +42,9 @@ struct DeviceState {
     bool ok = false;                // false => spmv() is a no-op
     bool has_empty_rows = false;
     bool vec_ok = true;             // ColIdx / Val 32-byte aligned: 128/256-bit loads allowed
+    long long dev_l2 = 0, dev_persist_max = 0, dev_window_max = 0, cur_persist = 0, cur_fetch = 0;
+    bool x_window = false;
+    const void *window_base = nullptr;
 
     // CSR on the device (owned upload, or the caller's device arrays adopted in place)
     int *rowptr = nullptr, *col = nullptr;
@@ -53,9 +56,15 @@ struct DeviceState {
 
     // Method_Parallel
     int tpr = 0;
-    // column bands (CSR_BANDED): band b covers columns [b*band_cols, (b+1)*band_cols)
+    // Active matrix view used by every layout builder and kernel: the CSR itself, or (x_bands > 1) its
+    // band-major copy, in which virtual row b*m + r holds the entries of row r whose column lies in band
+    // b = col / band_cols.  Kernels then write the virtual y (v_y) and band_reduce_kernel folds it.
+    int a_m = 0;
+    int *a_rowptr = nullptr, *a_col = nullptr;
+    void *a_val = nullptr;
     int x_bands = 1, band_cols = 0;
-    int *band_ptr = nullptr;        // int[x_bands * m + 1] : per (band,row) start into col/val
+    int *v_rowptr = nullptr, *v_col = nullptr;
+    void *v_val = nullptr, *v_y = nullptr;
     // Method_Balanced: row blocks; ref_splitter mirrors the reference with the caller's nthreads
     int parts = 0;
     int *splitter = nullptr, *ref_splitter = nullptr;

@@ -2,7 +2,7 @@
 //   csr_reforder_kernel   Method_Serial    (bit-identical summation order to the reference)
 //   csr_vector_kernel     Method_Parallel  (sub-warp per row, 128/256-bit streaming loads)
 //   row_block_kernel      Method_Balanced  (one warp per nnz-balanced row block of the csrSplitter)
-//   csr_banded_kernel     Method_Parallel with column bands (x band kept L2-resident)
+//   band_*_kernel         band-major ("virtual row") copy that keeps the gathered slice of x in L2
 #pragma once
 #include "common.cuh"
 
@@ -208,60 +208,59 @@ __global__ void fill_zero_kernel(long long n, T *__restrict__ y)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Column-banded CSR-vector (optional layout of Method_Parallel for matrices whose x does not fit
-// L2).  The non-zeros of every row are already sorted by column, so band b of row r is the
-// contiguous sub-range [band_ptr[b*m + r], band_ptr[(b+1)*m + r]) of the SAME ColIdx/Val arrays: no
-// copy of the matrix, only (K+1)*m extra row pointers.  One launch per band, in band order: every CTA of
-// a launch touches only x[b*band_cols, (b+1)*band_cols), which therefore stays L2-resident; y is
-// accumulated band by band in a fixed order (deterministic).
+// Band-major ("virtual row") copy of the matrix, built at handle construction when x does not fit the
+// part of L2 that random gathers can use (~half of the 126 MB: measured knee at 64 MiB, see
+// scripts/gather_probe.cu).  Columns are cut into K bands of band_cols; the entries of row r that fall
+// into band b become virtual row b*m + r of a CSR with K*m rows, stored band after band.  Any CSR
+// kernel then runs unchanged on the virtual matrix in ONE launch: CTAs are dispatched in row order, so
+// at any moment all resident CTAs work inside one band and gather from an L2-resident slice of x.
+// band_reduce_kernel adds the K partial vectors in band order (deterministic).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TPR, bool VEC>
-__global__ void __launch_bounds__(kThreads)
-csr_banded_kernel(int m, int nnz, int first, const int *__restrict__ bstart, const int *__restrict__ bend,
-                  const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
-                  T *__restrict__ y)
-{
-    const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
-    const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const long long row_l = gt / TPR;
-    const int sl = threadIdx.x & (TPR - 1);
-    const bool valid = row_l < m;
-    const int row = valid ? (int)row_l : 0;
-    const int start = valid ? bstart[row] : 0;
-    const int end = valid ? bend[row] : 0;
-    T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
-    sum = group_sum_c<T, TPR>(sum);
-    if (valid && sl == 0) {
-        if (first) y[row] = sum; else y[row] += sum;
-    }
-}
+constexpr int kMaxBands = 64;
 
-// band_ptr[b*m + r] = first position in row r whose column is >= b*band_cols (lower bound inside the
-// sorted row), b = 0..K; band K is the row end.
-__global__ void band_ptr_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
-                                const int *__restrict__ col, int *__restrict__ bptr)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)m * (bands + 1)) return;
-    const int b = (int)(i / m), r = (int)(i % m);
-    int lo = rowptr[r], hi = rowptr[r + 1];
-    if (b == bands) { bptr[i] = hi; return; }
-    const long long key = (long long)b * band_cols;
-    while (lo < hi) {
-        const int mid = (int)(((long long)lo + hi) >> 1);
-        if (col[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    bptr[i] = lo;
-}
-
-// 1 in *flag when some row has a column index smaller than its predecessor (banding needs sorted rows)
-__global__ void unsorted_rows_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                     int *__restrict__ flag)
+__global__ void band_count_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
+                                  const int *__restrict__ col, int *__restrict__ counts)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
-    for (int j = rowptr[r] + 1; j < rowptr[r + 1]; ++j)
-        if (col[j] < col[j - 1]) { *flag = 1; return; }
+    int cnt[kMaxBands];
+    for (int b = 0; b < bands; ++b) cnt[b] = 0;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+        int b = col[j] / band_cols;
+        b = b < 0 ? 0 : (b >= bands ? bands - 1 : b);
+        ++cnt[b];
+    }
+    for (int b = 0; b < bands; ++b) counts[(size_t)b * m + r] = cnt[b];
+}
+
+template <typename T>
+__global__ void band_scatter_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
+                                    const int *__restrict__ col, const T *__restrict__ val,
+                                    const int *__restrict__ vrowptr, int *__restrict__ vcol,
+                                    T *__restrict__ vval)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    int pos[kMaxBands];
+    for (int b = 0; b < bands; ++b) pos[b] = vrowptr[(size_t)b * m + r];
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) {  // stable: order inside a row is kept
+        const int c = col[j];
+        int b = c / band_cols;
+        b = b < 0 ? 0 : (b >= bands ? bands - 1 : b);
+        const int d = pos[b]++;
+        vcol[d] = c;
+        vval[d] = val[j];
+    }
+}
+
+template <typename T>
+__global__ void band_reduce_kernel(int m, int bands, const T *__restrict__ yv, T *__restrict__ y)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    T s = ldg_stream(yv + r);
+    for (int b = 1; b < bands; ++b) s += ldg_stream(yv + (size_t)b * m + r);
+    stg_y(y + r, s);
 }
 
 }  // namespace sb

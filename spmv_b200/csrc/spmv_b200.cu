@@ -7,6 +7,7 @@
 #include <mutex>
 #include <string>
 #include <map>
+#include <cmath>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -44,7 +45,8 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 struct Options {
     std::mutex mu;
     std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 16}, {"block_nnz", 512},
-                                       {"tile_items", 8},   {"tpr", 0},         {"x_bands", 1}};
+                                       {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
+                                       {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -123,7 +125,10 @@ static bool exclusive_scan(const V *in, V *out, int count, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------
 static void free_layouts(DeviceState *st)
 {
-    dfree(st->band_ptr); st->band_ptr = nullptr;
+    dfree(st->v_rowptr); st->v_rowptr = nullptr;
+    dfree(st->v_col); st->v_col = nullptr;
+    dfree(st->v_val); st->v_val = nullptr;
+    dfree(st->v_y); st->v_y = nullptr;
     dfree(st->splitter); st->splitter = nullptr;
     dfree(st->ref_splitter); st->ref_splitter = nullptr;
     dfree(st->tile_rows); st->tile_rows = nullptr;
@@ -156,6 +161,32 @@ static void free_state(DeviceState *st)
     delete st;
 }
 
+// Device-wide L2 controls (options l2_persist / l2_fetch), applied when a handle is created:
+//  * l2_persist: bytes of L2 set aside for evict-last ("persisting") lines, -1 = the device maximum.
+//    The evict-last hint on the x gathers only protects lines inside this carve-out.
+//  * l2_fetch: cudaLimitMaxL2FetchGranularity (32/64/128): bytes pulled from DRAM per L2 miss.
+static void apply_device_limits(DeviceState *st)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, st->device) != cudaSuccess) { cudaGetLastError(); return; }
+    st->dev_l2 = prop.l2CacheSize;
+    st->dev_persist_max = prop.persistingL2CacheMaxSize;
+    st->dev_window_max = prop.accessPolicyMaxWindowSize;
+    long long persist = opt("l2_persist");
+    if (persist != 0) {
+        size_t want = persist < 0 ? (size_t)prop.persistingL2CacheMaxSize : (size_t)persist;
+        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    }
+    const long long fetch = opt("l2_fetch");
+    if (fetch == 32 || fetch == 64 || fetch == 128)
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
+    size_t v = 0;
+    if (cudaDeviceGetLimit(&v, cudaLimitPersistingL2CacheSize) == cudaSuccess) st->cur_persist = (long long)v;
+    if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) == cudaSuccess) st->cur_fetch = (long long)v;
+    st->x_window = opt("x_window") != 0;
+}
+
 static int pick_tpr(long long nnz, int m)
 {
     const long long forced = opt("tpr");
@@ -166,41 +197,61 @@ static int pick_tpr(long long nnz, int m)
     return tpr;
 }
 
-static bool build_bands(DeviceState *st)
+// Decide the number of column bands and, when > 1, build the band-major copy and make it the active view.
+template <typename T>
+static bool build_band_major(DeviceState *st)
 {
-    long long bands = opt("x_bands");
-    if (bands <= 1 || st->m == 0 || st->nnz == 0) return true;
-    if (bands > 64) bands = 64;
-    int *flag = nullptr;
-    if (!dmalloc(&flag, 1)) return false;
-    SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
-    unsorted_rows_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(st->m, st->rowptr, st->col, flag);
-    int unsorted = 0;
-    const bool ok = read_flag(flag, st->stream, &unsorted);
-    dfree(flag);
-    if (!ok) return false;
-    if (unsorted) return true;  // rows not column-sorted: keep the plain CSR-vector kernel
-    st->x_bands = (int)bands;
-    st->band_cols = (int)(((long long)st->n + bands - 1) / bands);
-    if (!dmalloc(&st->band_ptr, (size_t)st->m * (bands + 1))) return false;
-    band_ptr_kernel<<<blocks_for((long long)st->m * (bands + 1)), kThreads, 0, st->stream>>>(
-        st->m, st->x_bands, st->band_cols, st->rowptr, st->col, st->band_ptr);
+    st->a_m = st->m; st->a_rowptr = st->rowptr; st->a_col = st->col; st->a_val = st->val;
+    if (st->m == 0 || st->nnz == 0) return true;
+    long long bands = opt("x_bands");  // 0 = automatic, 1 = off, >= 2 forced
+    const double xbytes = (double)st->n * st->vsize;
+    const double usable = st->dev_l2 > 0 ? 0.5 * (double)st->dev_l2 : 63.0 * 1048576.0;  // random-access reach
+    if (bands == 0) {
+        bands = 1;
+        if (xbytes > 0.9 * usable) {
+            long long k = (long long)ceil(xbytes / (0.75 * usable));
+            // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save
+            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
+        }
+    }
+    if (bands <= 1) return true;
+    if (bands > kMaxBands) bands = kMaxBands;
+    if ((long long)st->m * bands > 0x7fffffffLL - 8192) return true;
+    const int K = (int)bands, m = st->m;
+    const int band_cols = (int)(((long long)st->n + K - 1) / K);
+    const size_t vm = (size_t)m * K;
+    int *counts = nullptr;
+    if (!dmalloc(&counts, vm + 1) || !dmalloc(&st->v_rowptr, vm + 1 + 8) || !dmalloc(&st->v_col, (size_t)st->nnz + 8)) return false;
+    if (!SB_CUDA(cudaMalloc(&st->v_val, ((size_t)st->nnz + 8) * sizeof(T)))) return false;
+    if (!SB_CUDA(cudaMalloc(&st->v_y, vm * sizeof(T)))) return false;
+    SB_TRY(cudaMemsetAsync(counts + vm, 0, sizeof(int), st->stream));
+    band_count_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, counts);
     SB_TRY(cudaGetLastError());
-    st->kernel = SPMV_B200_KERNEL_CSR_BANDED;
+    const bool ok = exclusive_scan(counts, st->v_rowptr, (int)vm + 1, st->stream);
+    dfree(counts);
+    if (!ok) return false;
+    band_scatter_kernel<T><<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, (const T *)st->val,
+                                                                       st->v_rowptr, st->v_col, (T *)st->v_val);
+    SB_TRY(cudaGetLastError());
+    SB_TRY(cudaStreamSynchronize(st->stream));
+    st->x_bands = K;
+    st->band_cols = band_cols;
+    st->a_m = (int)vm; st->a_rowptr = st->v_rowptr; st->a_col = st->v_col; st->a_val = st->v_val;
+    st->vec_ok = true;
     return true;
 }
 
 // a9 on the device for `parts` partitions; *starved = some partition owns no whole row (a10)
-static bool build_splitter(DeviceState *st, int parts, int **out, int *starved)
+static bool build_splitter(DeviceState *st, int m, const int *rowptr, int parts, int **out, int *starved)
 {
     if (!dmalloc(out, (size_t)parts + 1)) return false;
-    splitter_kernel<<<blocks_for(parts + 1), kThreads, 0, st->stream>>>(parts, st->nnz, st->m, st->rowptr, *out);
+    splitter_kernel<<<blocks_for(parts + 1), kThreads, 0, st->stream>>>(parts, st->nnz, m, rowptr, *out);
     SB_TRY(cudaGetLastError());
     if (starved) {
         int *flag = nullptr;
         if (!dmalloc(&flag, 1)) return false;
         SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
-        splitter_starved_kernel<<<blocks_for(parts), kThreads, 0, st->stream>>>(parts, st->m, *out, flag);
+        splitter_starved_kernel<<<blocks_for(parts), kThreads, 0, st->stream>>>(parts, m, *out, flag);
         const bool ok = read_flag(flag, st->stream, starved);
         dfree(flag);
         if (!ok) return false;
@@ -214,17 +265,17 @@ static bool build_tiles(DeviceState *st, bool merge)
     if (ipt != 4 && ipt != 8) ipt = 8;
     st->tile_items = ipt;
     const long long per_tile = (long long)kThreads * ipt;
-    const long long total = merge ? (long long)st->m + st->nnz : (long long)st->nnz;
+    const long long total = merge ? (long long)st->a_m + st->nnz : (long long)st->nnz;
     st->tiles = (int)((total + per_tile - 1) / per_tile);
     if (st->tiles < 1) st->tiles = 1;
     if (merge) {
         if (!dmalloc(&st->merge_coords, (size_t)st->tiles + 1)) return false;
         merge_coords_kernel<<<blocks_for(st->tiles + 1), kThreads, 0, st->stream>>>(
-            st->tiles, (int)per_tile, st->nnz, st->m, st->rowptr, st->merge_coords);
+            st->tiles, (int)per_tile, st->nnz, st->a_m, st->a_rowptr, st->merge_coords);
     } else {
         if (!dmalloc(&st->tile_rows, (size_t)st->tiles + 1)) return false;
         tile_rows_kernel<<<blocks_for(st->tiles + 1), kThreads, 0, st->stream>>>(
-            st->tiles, (int)per_tile, st->nnz, st->m, st->rowptr, st->tile_rows);
+            st->tiles, (int)per_tile, st->nnz, st->a_m, st->a_rowptr, st->tile_rows);
     }
     SB_TRY(cudaGetLastError());
     if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)st->tiles * st->vsize))) return false;
@@ -241,17 +292,17 @@ static bool build_sell(DeviceState *st)
     if (sigma > kSellMaxSigma) sigma = kSellMaxSigma;
     sigma = (sigma / kSellC) * kSellC;
     st->sigma = (int)sigma;
-    const int windows = st->m / st->sigma;
+    const int windows = st->a_m / st->sigma;
     st->banner = windows * st->sigma;  // reference sell_C_Sigma_spmv.c:148-156
     st->slices = st->banner / kSellC;
-    st->tpr = pick_tpr(st->nnz, st->m);  // for the CSR tail rows [banner, m)
+    st->tpr = pick_tpr(st->nnz, st->a_m);  // for the CSR tail rows [banner, m)
     st->kernel = SPMV_B200_KERNEL_SELL;
     if (st->banner == 0) return true;
     int pow2 = 1;
     while (pow2 < st->sigma) pow2 <<= 1;
     if (!dmalloc(&st->sell_perm, (size_t)st->banner)) return false;
     sell_sort_kernel<<<windows, kThreads, (size_t)pow2 * sizeof(unsigned long long), st->stream>>>(
-        st->sigma, pow2, st->rowptr, st->sell_perm);
+        st->sigma, pow2, st->a_rowptr, st->sell_perm);
     SB_TRY(cudaGetLastError());
     long long *count = nullptr;
     if (!dmalloc(&st->sell_width, (size_t)st->slices) || !dmalloc(&st->sell_full, (size_t)st->slices) ||
@@ -259,7 +310,7 @@ static bool build_sell(DeviceState *st)
         return false;
     SB_TRY(cudaMemsetAsync(count, 0, ((size_t)st->slices + 1) * sizeof(long long), st->stream));
     sell_width_kernel<<<blocks_for((long long)st->slices * 32), kThreads, 0, st->stream>>>(
-        st->slices, st->rowptr, st->sell_perm, st->sell_width, st->sell_full, count);
+        st->slices, st->a_rowptr, st->sell_perm, st->sell_width, st->sell_full, count);
     SB_TRY(cudaGetLastError());
     const bool ok = exclusive_scan(count, st->sell_slice_ptr, st->slices + 1, st->stream);
     dfree(count);
@@ -268,7 +319,7 @@ static bool build_sell(DeviceState *st)
     if (!dmalloc(&st->sell_col, (size_t)st->padded)) return false;
     if (!SB_CUDA(cudaMalloc(&st->sell_val, (size_t)(st->padded ? st->padded : 1) * sizeof(T)))) return false;
     sell_fill_kernel<T><<<blocks_for((long long)st->slices * 32), kThreads, 0, st->stream>>>(
-        st->slices, st->rowptr, st->col, (const T *)st->val, st->sell_perm, st->sell_slice_ptr, st->sell_col,
+        st->slices, st->a_rowptr, st->a_col, (const T *)st->a_val, st->sell_perm, st->sell_slice_ptr, st->sell_col,
         (T *)st->sell_val);
     SB_TRY(cudaGetLastError());
     return true;
@@ -300,11 +351,11 @@ static bool build_csr5(DeviceState *st)
         !dmalloc(&st->c5_tile_desc, (size_t)p * kC5Omega) || !dmalloc(&off_cnt, (size_t)p + 1) ||
         !dmalloc(&st->c5_off_ptr, (size_t)p + 1))
         return false;
-    c5_tile_ptr_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, sigma, st->nnz, st->m, st->rowptr, raw);
-    c5_tile_dirty_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, st->m, st->rowptr, raw, st->c5_tile_ptr);
+    c5_tile_ptr_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, sigma, st->nnz, st->a_m, st->a_rowptr, raw);
+    c5_tile_dirty_kernel<<<blocks_for(p + 1), kThreads, 0, st->stream>>>(p, st->a_m, st->a_rowptr, raw, st->c5_tile_ptr);
     SB_TRY(cudaMemsetAsync(off_cnt, 0, ((size_t)p + 1) * sizeof(int), st->stream));
     c5_tile_desc_kernel<<<blocks_for((long long)p * 32), kThreads, 0, st->stream>>>(
-        p, sigma, by, bs, st->rowptr, st->c5_tile_ptr, st->c5_tile_desc, off_cnt);
+        p, sigma, by, bs, st->a_rowptr, st->c5_tile_ptr, st->c5_tile_desc, off_cnt);
     SB_TRY(cudaGetLastError());
     bool ok = exclusive_scan(off_cnt, st->c5_off_ptr, p + 1, st->stream);
     dfree(raw);
@@ -318,13 +369,13 @@ static bool build_csr5(DeviceState *st)
         if (!dmalloc(&st->c5_off, (size_t)st->c5_num_offsets)) return false;
         SB_TRY(cudaMemsetAsync(st->c5_off, 0, (size_t)st->c5_num_offsets * sizeof(int), st->stream));
         c5_desc_offset_kernel<<<blocks_for((long long)p * 32), kThreads, 0, st->stream>>>(
-            p, sigma, by, bs, st->rowptr, st->c5_tile_ptr, st->c5_tile_desc, st->c5_off_ptr, st->c5_off);
+            p, sigma, by, bs, st->a_rowptr, st->c5_tile_ptr, st->c5_tile_desc, st->c5_off_ptr, st->c5_off);
         SB_TRY(cudaGetLastError());
     }
     if (!dmalloc(&st->c5_col, (size_t)st->nnz)) return false;
     if (!SB_CUDA(cudaMalloc(&st->c5_val, (size_t)st->nnz * sizeof(T)))) return false;
     c5_transpose_kernel<T><<<blocks_for(st->nnz), kThreads, 0, st->stream>>>(
-        st->nnz, sigma, p, st->c5_tile_ptr, st->col, (const T *)st->val, st->c5_col, (T *)st->c5_val);
+        st->nnz, sigma, p, st->c5_tile_ptr, st->a_col, (const T *)st->a_val, st->c5_col, (T *)st->c5_val);
     SB_TRY(cudaGetLastError());
     if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)p * sizeof(T)))) return false;
     if (!dmalloc(&st->carry_row, (size_t)p)) return false;
@@ -339,16 +390,16 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
         st->kernel = SPMV_B200_KERNEL_CSR_REFORDER;
         return true;
     case Method_Parallel:
-        st->tpr = pick_tpr(st->nnz, st->m);
+        st->tpr = pick_tpr(st->nnz, st->a_m);
         st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
-        return build_bands(st);
+        return true;
     case Method_Balanced:
     case Method_Balanced2: {
         // mirror of the reference's demotion / promotion rule with the CALLER's nthreads (a10,
         // parallel_balanced2_spmv.c:72-94) for clients that read handle->spmvMethod
         st->ref_T = (int)(h->nthreads ? (h->nthreads > (1u << 24) ? (1u << 24) : h->nthreads) : 1);
         int ref_starved = 0;
-        if (!build_splitter(st, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
+        if (!build_splitter(st, st->m, st->rowptr, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
         h->spmvMethod = ref_starved ? Method_Balanced2 : Method_Balanced;
         // the GPU geometry: row blocks of ~block_nnz non-zeros, one warp each
         long long block_nnz = opt("block_nnz");
@@ -356,7 +407,7 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
         st->parts = (int)(((long long)st->nnz + block_nnz - 1) / block_nnz);
         if (st->parts < 1) st->parts = 1;
         int starved = 0;
-        if (!build_splitter(st, st->parts, &st->splitter, &starved)) return false;
+        if (!build_splitter(st, st->a_m, st->a_rowptr, st->parts, &st->splitter, &starved)) return false;
         // Balanced2 was asked for, or a row is long enough to starve a row block: merge-path
         if (method == Method_Balanced2 || starved) return build_tiles(st, /*merge=*/true);
         st->kernel = SPMV_B200_KERNEL_ROW_BLOCKS;
@@ -384,6 +435,7 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
         return false;
     }
     SB_TRY(cudaGetDevice(&st->device));
+    apply_device_limits(st);
     if (m < 0 || n < 0 || (m > 0 && (!RowPtr))) { set_error("invalid arguments (m=%d n=%d RowPtr=%p)", m, n, (void *)RowPtr); return false; }
     st->m = m;
     st->n = n;
@@ -427,11 +479,16 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
     }
     st->vec_ok = (((uintptr_t)st->col | (uintptr_t)st->val) & 31u) == 0;
 
+    st->a_m = st->m; st->a_rowptr = st->rowptr; st->a_col = st->col; st->a_val = st->val;
+    if (method != Method_Serial) {  // Method_Serial keeps the reference's exact summation order: never banded
+        const bool okb = st->vsize == 8 ? build_band_major<double>(st) : build_band_major<float>(st);
+        if (!okb) return false;
+    }
     if (m > 0) {
         int *flag = nullptr;
         if (!dmalloc(&flag, 1)) return false;
         SB_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st->stream));
-        empty_rows_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->rowptr, flag);
+        empty_rows_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, st->a_rowptr, flag);
         int e = 0;
         const bool ok = read_flag(flag, st->stream, &e);
         dfree(flag);
@@ -454,30 +511,12 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
 template <typename T, bool VEC>
 static void launch_vector(DeviceState *st, int tpr, const T *x, T *y)
 {
-    const int m = st->m;
+    const int m = st->a_m;
     const int grid = blocks_for((long long)m * tpr);
-#define SB_CASE(N) case N: csr_vector_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->rowptr, st->col, (const T *)st->val, x, y); break;
+#define SB_CASE(N) case N: csr_vector_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y); break;
     switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
 #undef SB_CASE
     count_launch();
-}
-
-template <typename T, bool VEC>
-static void launch_banded(DeviceState *st, const T *x, T *y)
-{
-    const int m = st->m;
-    // lanes per row sized for a band's share of the row
-    int tpr = 1;
-    const double mean = (double)st->nnz / m / st->x_bands;
-    while (tpr < 32 && 4.0 * tpr < mean) tpr <<= 1;
-    const int grid = blocks_for((long long)m * tpr);
-    for (int b = 0; b < st->x_bands; ++b) {
-        const int *bs = st->band_ptr + (size_t)b * m, *be = st->band_ptr + (size_t)(b + 1) * m;
-#define SB_CASE(N) case N: csr_banded_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, b == 0, bs, be, st->col, (const T *)st->val, x, y); break;
-        switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
-#undef SB_CASE
-    }
-    count_launch(st->x_bands);
 }
 
 // CSR-vector over rows [row0, m) only (the CSR tail of SELL)
@@ -498,51 +537,50 @@ csr_tail_kernel(int row0, int m, const int *__restrict__ rowptr, const int *__re
 }
 
 template <typename T>
-static bool launch(DeviceState *st, const T *x, T *y)
+static bool launch(DeviceState *st, const T *x, T *y_out)
 {
     cudaStream_t s = st->stream;
-    const int m = st->m;
-    if (m == 0) return true;
+    if (st->m == 0) return true;
     if (st->kernel == SPMV_B200_KERNEL_NONE) {  // nnz == 0: y = 0
-        fill_zero_kernel<T><<<blocks_for(m), kThreads, 0, s>>>(m, y);
+        fill_zero_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out);
         count_launch();
         return SB_CUDA(cudaGetLastError());
     }
-    const T *val = (const T *)st->val;
+    // the active view: the CSR itself, or its band-major copy writing the virtual y
+    const int m = st->a_m;
+    T *y = st->x_bands > 1 ? (T *)st->v_y : y_out;
+    const T *val = (const T *)st->a_val;
     switch (st->kernel) {
     case SPMV_B200_KERNEL_CSR_REFORDER: {
         constexpr int L = sizeof(T) == 8 ? 4 : 8;
-        csr_reforder_kernel<T><<<blocks_for((long long)m * L), kThreads, 0, s>>>(m, st->rowptr, st->col, val, x, y);
+        csr_reforder_kernel<T><<<blocks_for((long long)m * L), kThreads, 0, s>>>(m, st->a_rowptr, st->a_col, val, x, y);
         count_launch();
         break;
     }
     case SPMV_B200_KERNEL_CSR_VECTOR:
         if (st->vec_ok) launch_vector<T, true>(st, st->tpr, x, y); else launch_vector<T, false>(st, st->tpr, x, y);
         break;
-    case SPMV_B200_KERNEL_CSR_BANDED:
-        if (st->vec_ok) launch_banded<T, true>(st, x, y); else launch_banded<T, false>(st, x, y);
-        break;
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
         const int grid = blocks_for((long long)st->parts * 32);
-        if (st->vec_ok) row_block_kernel<T, true><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->rowptr, st->col, val, x, y);
-        else row_block_kernel<T, false><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->rowptr, st->col, val, x, y);
+        if (st->vec_ok) row_block_kernel<T, true><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y);
+        else row_block_kernel<T, false><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y);
         count_launch();
         break;
     }
     case SPMV_B200_KERNEL_MERGE_PATH: {
         if (st->tile_items == 4)
-            merge_path_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+            merge_path_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         else
-            merge_path_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+            merge_path_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
         count_launch(2);
         break;
     }
     case SPMV_B200_KERNEL_NNZ_SPLIT: {
         if (st->tile_items == 4)
-            nnz_split_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+            nnz_split_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         else
-            nnz_split_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->rowptr, st->col, val, x, y, (T *)st->carry_val, st->carry_row);
+            nnz_split_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
         count_launch(2);
         break;
@@ -554,7 +592,7 @@ static bool launch(DeviceState *st, const T *x, T *y)
             count_launch();
         }
         if (st->banner < m) {
-            csr_tail_kernel<T><<<blocks_for((long long)(m - st->banner) * 32), kThreads, 0, s>>>(st->banner, m, st->rowptr, st->col, val, x, y);
+            csr_tail_kernel<T><<<blocks_for((long long)(m - st->banner) * 32), kThreads, 0, s>>>(st->banner, m, st->a_rowptr, st->a_col, val, x, y);
             count_launch();
         }
         break;
@@ -575,7 +613,7 @@ static bool launch(DeviceState *st, const T *x, T *y)
         }
         const int tail_nz0 = (p - 1) * kC5Omega * st->c5_sigma;
         csr5_tail_kernel<T><<<blocks_for((long long)(m - st->c5_tail_start) * 32), kThreads, 0, s>>>(
-            m, st->c5_tail_start, tail_nz0, p - 1, st->rowptr, st->c5_col, tval, x, y, (T *)st->carry_val, st->carry_row);
+            m, st->c5_tail_start, tail_nz0, p - 1, st->a_rowptr, st->c5_col, tval, x, y, (T *)st->carry_val, st->carry_row);
         carry_fixup_kernel<T><<<blocks_for(p), kThreads, 0, s>>>(p, st->carry_row, (const T *)st->carry_val, y);
         count_launch(2);
         break;
@@ -583,6 +621,10 @@ static bool launch(DeviceState *st, const T *x, T *y)
     default:
         set_error("handle has no kernel (%d)", st->kernel);
         return false;
+    }
+    if (st->x_bands > 1) {
+        band_reduce_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out);
+        count_launch();
     }
     return SB_CUDA(cudaGetLastError());
 }
@@ -680,6 +722,19 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
         if (!st->y_stage && !SB_CUDA(cudaMalloc(&st->y_stage, yb ? yb : 1))) return;
         yd = st->y_stage;
     }
+    if (st->x_window && xd != st->window_base && xb) {
+        // optional: mark x as persisting for everything launched on this stream
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = const_cast<void *>(xd);
+        attr.accessPolicyWindow.num_bytes = xb < (size_t)st->dev_window_max ? xb : (size_t)st->dev_window_max;
+        const double room = st->cur_persist > 0 ? (double)st->cur_persist / (double)attr.accessPolicyWindow.num_bytes : 0.0;
+        attr.accessPolicyWindow.hitRatio = room >= 1.0 ? 1.0f : (float)room;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        st->window_base = xd;
+    }
     const bool ok = st->vsize == 8 ? launch<double>(st, (const double *)xd, (double *)yd)
                                    : launch<float>(st, (const float *)xd, (float *)yd);
     if (!ok) return;
@@ -766,8 +821,15 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "device") return st->device;
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
+    if (k == "band_cols") return st->band_cols;
+    if (k == "active_rows") return st->a_m;
     if (k == "owns_csr") return st->owns_csr;
     if (k == "vec_ok") return st->vec_ok;
+    if (k == "dev_l2_bytes") return st->dev_l2;
+    if (k == "dev_persist_max") return st->dev_persist_max;
+    if (k == "dev_window_max") return st->dev_window_max;
+    if (k == "l2_persist_bytes") return st->cur_persist;
+    if (k == "l2_fetch_bytes") return st->cur_fetch;
     return -1;
 }
 
@@ -794,7 +856,8 @@ long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst,
     else if (k == "csr5_offsets") { src = st->c5_off; bytes = (size_t)st->c5_num_offsets * 4; }
     else if (k == "csr5_col") { src = st->c5_col; bytes = (size_t)st->nnz * 4; }
     else if (k == "csr5_val") { src = st->c5_val; bytes = (size_t)st->nnz * st->vsize; }
-    else if (k == "band_ptr") { src = st->band_ptr; bytes = st->band_ptr ? (size_t)st->m * (st->x_bands + 1) * 4 : 0; }
+    else if (k == "band_rowptr") { src = st->v_rowptr; bytes = st->v_rowptr ? ((size_t)st->a_m + 1) * 4 : 0; }
+    else if (k == "band_col") { src = st->v_col; bytes = st->v_col ? (size_t)st->nnz * 4 : 0; }
     else return -1;
     if (!src) bytes = 0;
     if (!dst || bytes == 0) return (long long)bytes;

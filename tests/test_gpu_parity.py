@@ -153,3 +153,29 @@ def test_balanced_demotion_rule_mirrors_reference(libpath, port):
                 assert h.struct.spmvMethod == (api.Method_Balanced if use_bal else api.Method_Balanced2), (name, T, req)
                 assert np.array_equal(h.structure("ref_splitter", np.int32), port.splitter(a.rowptr, T))
                 h.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+@pytest.mark.parametrize("bands", [2, 5])
+def test_band_major_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
+    """The band-major (virtual-row) copy under every method: same bound, reproducible; Method_Serial is
+    never banded and stays bit-identical to the reference."""
+    for name in ("uni32", "skew", "hub", "lead_trail_empty", "lap48", "rmat12"):
+        a = CASES[name]().astype(dt)
+        x = M.make_x(a.n, 99, dt)
+        for method in METHODS:
+            api.set_option("x_bands", bands)
+            try:
+                h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+            finally:
+                api.set_option("x_bands", 0)
+            assert h.info("x_bands") == (1 if method == api.Method_Serial else bands)
+            y = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y)
+            tag = f"bands{bands}/{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
+            assert not np.isnan(y).any(), tag
+            check_y(port, serial_ref, a, x, y, method, tag)
+            y2 = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y2)
+            assert bits_equal(y, y2), tag
+            h.destroy()

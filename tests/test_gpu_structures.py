@@ -127,3 +127,24 @@ def test_generators_match_numpy_bit_for_bit(libpath):
         x = torch.empty(5000, dtype=dt, device="cuda:0")
         api.gen_x(x, 5000, 77, False, size)
         assert bits_equal(x.cpu().numpy(), M.make_x(5000, 77, np.float64 if size == 8 else np.float32))
+
+
+@pytest.mark.parametrize("name", ["uni32", "skew", "hub", "lap48", "lead_trail_empty"])
+def test_band_major_copy_is_a_stable_column_bucketing(libpath, name):
+    a = CASES[name]()
+    for K in (2, 3, 7):
+        api.set_option("x_bands", K)
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
+        api.set_option("x_bands", 0)
+        assert h.info("x_bands") == K and h.info("active_rows") == K * a.m
+        bc = h.info("band_cols")
+        assert bc == -(-a.n // K)
+        vr = h.structure("band_rowptr", np.int32)
+        vc = h.structure("band_col", np.int32)
+        rows = np.repeat(np.arange(a.m), np.diff(a.rowptr))
+        band = np.minimum(a.col // bc, K - 1)
+        order = np.lexsort((np.arange(a.nnz), rows, band))      # band-major, row, original order (stable)
+        assert np.array_equal(vc, a.col[order])
+        cnt = np.bincount(band.astype(np.int64) * a.m + rows, minlength=K * a.m)
+        assert np.array_equal(vr, np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32))
+        h.destroy()
