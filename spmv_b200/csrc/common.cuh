@@ -63,6 +63,7 @@ struct DeviceState {
     int *a_rowptr = nullptr, *a_col = nullptr;
     void *a_val = nullptr;
     int x_bands = 1, band_cols = 0;
+    double far_fraction = -1.0;     // share of entries far from the diagonal (automatic band decision)
     int *v_rowptr = nullptr, *v_col = nullptr;
     void *v_val = nullptr, *v_y = nullptr;
     // Method_Balanced: row blocks; ref_splitter mirrors the reference with the caller's nthreads

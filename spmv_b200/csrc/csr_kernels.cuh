@@ -157,7 +157,7 @@ row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int
     const int nz = rowptr[r1] - rowptr[r0];
     const int avg = (nz + nrows - 1) / nrows;
     int tpr = 1;
-    while (tpr < 32 && 4 * tpr < avg) tpr <<= 1;
+    while (tpr < 32 && 7 * tpr < avg) tpr <<= 1;
     const int rows_per_iter = 32 / tpr;
     const int sub = lane / tpr, sl = lane & (tpr - 1);
     const int nnz4 = nnz & ~3;
@@ -217,6 +217,26 @@ __global__ void fill_zero_kernel(long long n, T *__restrict__ y)
 // band_reduce_kernel adds the K partial vectors in band order (deterministic).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxBands = 64;
+
+// Locality probe for the automatic band decision: how many entries lie further than `halfwidth` columns
+// from their row's position on the (scaled) diagonal?  Stencil / banded / FEM matrices answer "almost
+// none" -- the rows in flight at any moment already share a small window of x and banding would only
+// manufacture empty virtual rows; uniform-random or graph matrices answer "almost all".
+__global__ void band_locality_kernel(int m, double cols_per_row, int halfwidth, const int *__restrict__ rowptr,
+                                     const int *__restrict__ col, unsigned long long *__restrict__ far_count)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long far = 0;
+    if (r < m) {
+        const long long diag = (long long)((double)r * cols_per_row);
+        for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+            const long long d = (long long)col[j] - diag;
+            far += (d > halfwidth || d < -halfwidth);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) far += __shfl_xor_sync(kFull, far, o);
+    if ((threadIdx.x & 31) == 0 && far) atomicAdd(far_count, far);  // integer counter, builder only
+}
 
 __global__ void band_count_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
                                   const int *__restrict__ col, int *__restrict__ counts)

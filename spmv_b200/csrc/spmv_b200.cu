@@ -193,7 +193,9 @@ static int pick_tpr(long long nnz, int m)
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return (int)forced;
     const double mean = m > 0 ? (double)nnz / m : 0.0;
     int tpr = 1;
-    while (tpr < 32 && 4.0 * tpr < mean) tpr <<= 1;  // each lane takes 4-element chunks
+    // measured on B200 (scripts/sweep.py): ~7 entries per lane is the sweet spot -- fewer lanes per row
+    // means more independent x gathers in flight per thread (mean 5 -> 1, 10.7 -> 2, 27 -> 4, 32 -> 8)
+    while (tpr < 32 && 7.0 * tpr < mean) tpr <<= 1;
     return tpr;
 }
 
@@ -211,7 +213,20 @@ static bool build_band_major(DeviceState *st)
         if (xbytes > 0.9 * usable) {
             long long k = (long long)ceil(xbytes / (0.75 * usable));
             // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save
-            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
+            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0) {
+                // ... and band only when the accesses are NOT already diagonal-local
+                unsigned long long *far = nullptr, h_far = 0;
+                if (!dmalloc(&far, 1)) return false;
+                SB_TRY(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
+                const int halfwidth = (int)(0.125 * usable / st->vsize);
+                band_locality_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(
+                    st->m, (double)st->n / st->m, halfwidth, st->rowptr, st->col, far);
+                SB_TRY(cudaMemcpyAsync(&h_far, far, sizeof(h_far), cudaMemcpyDeviceToHost, st->stream));
+                SB_TRY(cudaStreamSynchronize(st->stream));
+                dfree(far);
+                st->far_fraction = (double)h_far / (double)st->nnz;
+                if (st->far_fraction > 0.25) bands = k;
+            }
         }
     }
     if (bands <= 1) return true;
@@ -822,6 +837,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
     if (k == "band_cols") return st->band_cols;
+    if (k == "far_permille") return (long long)(st->far_fraction * 1000.0);
     if (k == "active_rows") return st->a_m;
     if (k == "owns_csr") return st->owns_csr;
     if (k == "vec_ok") return st->vec_ok;
