@@ -6,9 +6,11 @@
 
 A "step" is one spmv() over the whole (per-rank) matrix.  N=1 runs BASELINE.json configs[1]
 (uniform-random 2^24 x 2^24, 32 nnz/row, fp64: "C2"); N>1 is weak scaling of the same shard: the global
-matrix has N*2^24 rows and columns, every rank owns 2^24 rows (equal nnz = the reference's splitter),
-x (N*128 MiB) is replicated, no collective on the data path.  The y->x power-method loop with its NCCL
-all-gather is timed separately and reported under "power_method".
+matrix has N*2^24 rows over the same 2^24 columns, every rank owns 2^24 rows (equal nnz = the reference's
+splitter), x (128 MiB) is replicated, no collective on the data path.  The y->x power-method loop is a
+separate leg on the SQUARE C2 matrix row-sharded over the N GPUs (strong scaling, 2^24/N rows each): once
+with an in-place NCCL all-gather timed apart from the SpMV ("power_method") and once with the all-gather
+fused into the SpMV epilogue as NVLink peer stores ("power_method_fused").
 
 One JSON line on stdout (rank 0).  `value` = whole-job GFLOP/s with everything resident in HBM;
 `e2e` = the same metric through the C-ABI with HOST x / y (pinned), H2D + kernel + D2H inside the timed
@@ -45,8 +47,10 @@ def make_workload(name: str, rank: int, world: int, small: bool):
     from spmv_b200 import api, matrices as M
     sh = 6 if small else 0  # --small: 64x fewer rows, for debugging the script itself
     if name == "c2":
+        # weak scaling: every GPU gets a full C2's worth of rows (2^24 x 32 nnz) of the (N*2^24) x 2^24
+        # matrix; x (128 MiB) is the same replicated vector at every N, so per-GPU work is identical
         rows = 1 << (LOG2_ROWS_C2 - sh)
-        n = rows * world
+        n = rows
         A = api.gen_uniform(rows, n, 32, M.SEED_C2, rank * rows, False, 8)
         desc = f"C2 uniform-random {rows * world}x{n}, 32 nnz/row, fp64 CSR ({rows} rows/GPU)"
         return A, n, 8, desc, M.SEED_C2
@@ -155,7 +159,9 @@ def cpu_time_reference(steps: int, warmup: int, small: bool, budget_s: float = 2
     flops = 2.0 * A.nnz
     if O.have_reference():
         R = O.Reference()
-        T = R.max_threads()
+        # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly,
+        # the reference sizes its team from omp_set_num_threads, src/samples/test_spmv.c:88)
+        T = max(R.max_threads(), len(os.sched_getaffinity(0)))
         best = None
         # spin the OpenMP team up first: the first ~second of parallel regions in a fresh process runs
         # 100x slow on these hosts (thread creation + cgroup ramp-up) and would bias the method choice
@@ -196,7 +202,9 @@ def cpu_time_reference(steps: int, warmup: int, small: bool, budget_s: float = 2
                                              "Method_BalancedYid", "Method_SellCSigma", "Method_Csr5Spmv"][method]
     else:
         P = O.Port()
-        T = os.cpu_count() or 1
+        T = len(os.sched_getaffinity(0))
+        C_omp = __import__("ctypes").CDLL("libgomp.so.1")
+        C_omp.omp_set_num_threads(T)
         y = P.spmv_serial(A.rowptr, A.col, A.val, x, parallel=True)
         t0 = time.perf_counter()
         P.spmv_serial(A.rowptr, A.col, A.val, x, parallel=True)
@@ -362,23 +370,50 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     assert torch.equal(y_chk.cpu(), hy), "host-pointer path and device-pointer path disagree"
 
-    # ---- power method: x <- A x with the y slices all-gathered (NCCL) into the next x ----
-    power = None
-    if args.power_iters > 0 and m * world == n:
+    # ---- power method on the SQUARE matrix of the workload, row-sharded over the ranks (strong scaling) ----
+    power = fused = None
+    if args.power_iters > 0 and args.workload in ("c2", "c5"):
         from spmv_b200 import multigpu as G
-        split = [g * m for g in range(world + 1)]
-        hp = handles[primary]
-        pm = G.PowerMethod(lambda xf, ys: hp.spmv(xf, ys), split, x)
+        if world == 1 or args.workload == "c5":
+            Ap, hp, mp = A, handles[primary], m          # the main shard already is a slice of a square matrix
+        else:
+            mp = n // world                               # rows [rank*n/N, (rank+1)*n/N) of the SAME C2 matrix
+            Ap = api.gen_uniform(mp, n, 32, seed, rank * mp, False, vsize)
+            hp = Ap.handle(METHODS[primary])
+        split = [g * mp for g in range(world + 1)]
+        xs = x * (1.0 / 16.0)  # un-normalised loop: keep 50 iterations far inside the fp64 range
+        pm = G.PowerMethod(lambda xf, ys: hp.spmv(xf, ys), split, xs)
         pm.run(2)
-        _, t_spmv, t_comm = pm.run(args.power_iters)
+        x_nccl, t_spmv, t_comm = pm.run(args.power_iters)
         if dist is not None:
             t = torch.tensor([t_spmv, t_comm], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_spmv, t_comm = (float(v) for v in t.tolist())
-        power = {"iters": args.power_iters, "spmv_ms_per_iter": t_spmv, "allgather_ms_per_iter": t_comm,
-                 "allgather_bytes_recv_per_gpu": (world - 1) * m * vsize,
+        power = {"iters": args.power_iters, "rows_per_gpu": mp, "kernel": hp.kernel, "spmv_ms_per_iter": t_spmv,
+                 "allgather_ms_per_iter": t_comm, "allgather_bytes_recv_per_gpu": (world - 1) * mp * vsize,
                  "collective": "ncclAllGather in place (torch.distributed)" if world > 1 else "none (1 GPU)",
                  "normalised": False}
+        try:
+            fp = G.FusedPowerMethod(hp, split, xs)
+            fp.run(2)
+            fp2 = G.FusedPowerMethod(hp, split, xs)
+            t_f, t_sync = fp2.run(args.power_iters + 2)
+            same = bool(torch.equal(fp2.result(), x_nccl))
+            if dist is not None:
+                t = torch.tensor([t_f, t_sync, 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t_f, t_sync, bad = (float(v) for v in t.tolist())
+                same = bad == 0.0
+            fused = {"iters": args.power_iters + 2, "spmv_plus_peer_stores_ms_per_iter": t_f, "rank_sync_ms_per_iter": t_sync,
+                     "peer_bytes_sent_per_gpu": (world - 1) * mp * vsize, "bitwise_equal_to_nccl_loop": same,
+                     "transport": "st.global to CUDA-IPC peer mappings over NVLink from the SpMV epilogue"}
+            fp.close()
+            fp2.close()
+        except Exception as e:  # IPC may be unavailable in some containers: the NCCL leg stands
+            log("fused power method unavailable:", repr(e))
+        if hp is not handles[primary]:
+            hp.destroy()
+            Ap.destroy()
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only, bounded sample) ----
     cpu = None
@@ -420,6 +455,8 @@ def run_gpu_arm(args):
             line["l2_warm"] = warm
         if power:
             line["power_method"] = power
+        if fused:
+            line["power_method_fused"] = fused
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

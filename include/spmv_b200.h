@@ -47,6 +47,8 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "l2_persist"      bytes of L2 set aside for persisting lines at create (0 = leave, -1 = device max)
  *   "l2_fetch"        cudaLimitMaxL2FetchGranularity at create (0 = leave; 32 / 64 / 128)
  *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
+ *   "force_merge"     1 = Method_Balanced2 always runs the merge-path kernel (default: only when a row is
+ *                     long enough to starve a row block, the reference's own Balanced2 -> Balanced rule)
  * Returns 0, or -1 for an unknown key. */
 SPMV_B200_API int spmv_b200_set_option(const char *key, long long value);
 SPMV_B200_API long long spmv_b200_get_option(const char *key);
@@ -85,6 +87,22 @@ SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
  * reference's init_csrSplitter_balanced2 (parallel_balanced2_spmv.c:41-53) with nthreads = parts.
  * RowPtr is a HOST pointer; pure host code, usable without a GPU.  Returns 0 or -1. */
 SPMV_B200_API int spmv_b200_partition_rows(const int *RowPtr, int m, int parts, int *splitter_out);
+
+/* ---- fused SpMV + all-gather over NVLink peer memory -----------------------------------------------
+ * In the iterated x <- A x loop on several GPUs every rank's y slice must reach every rank's next x.
+ * Instead of a separate collective, a handle can store each y value to up to 8 EXTRA destinations while
+ * it computes: device_ptrs[i] is the address where this rank's slice starts inside peer i's next-x buffer
+ * (a peer mapping obtained through spmv_b200_ipc_open, or any local device buffer).  The stores are
+ * issued by the kernel that produces the final y (CSR-vector, row blocks, SELL, the band reduce); the other
+ * kernel families fall back to one stream-ordered copy kernel.  count = 0 switches it off.  The caller
+ * synchronises the ranks (e.g. a 1-element NCCL all-reduce) before the next x is read.
+ * ipc_export writes a 64-byte handle for a pointer returned by spmv_b200_malloc; ipc_open maps a handle
+ * exported by another process on the same node (peer access is enabled lazily).  Return 0 / pointer, or
+ * -1 / NULL with spmv_b200_last_error() set. */
+SPMV_B200_API int spmv_b200_set_y_peers(spmv_Handle_t handle, int count, void *const *device_ptrs);
+SPMV_B200_API int spmv_b200_ipc_export(const void *device_ptr, void *handle_out_64);
+SPMV_B200_API void *spmv_b200_ipc_open(const void *handle_64);
+SPMV_B200_API int spmv_b200_ipc_close(void *opened_ptr);
 
 /* ---- device memory helpers for C clients (Python clients use torch tensors) ----------------------- */
 SPMV_B200_API void *spmv_b200_malloc(size_t bytes);

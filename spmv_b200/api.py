@@ -35,7 +35,8 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_sync", "spmv_b200_set_option", "spmv_b200_get_option", "spmv_b200_info",
     "spmv_b200_structure", "spmv_b200_launch_count", "spmv_b200_partition_rows", "spmv_b200_malloc",
     "spmv_b200_free", "spmv_b200_memcpy", "spmv_b200_gen_laplacian2d", "spmv_b200_gen_stencil27",
-    "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free"]
+    "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free",
+    "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -98,6 +99,11 @@ def lib() -> C.CDLL:
     L.spmv_b200_free.argtypes = [vp]
     L.spmv_b200_free.restype = None
     L.spmv_b200_memcpy.argtypes = [vp, vp, C.c_size_t, i]
+    L.spmv_b200_set_y_peers.argtypes = [spmv_Handle_t, i, C.POINTER(vp)]
+    L.spmv_b200_ipc_export.argtypes = [vp, C.c_char_p]
+    L.spmv_b200_ipc_open.argtypes = [C.c_char_p]
+    L.spmv_b200_ipc_open.restype = vp
+    L.spmv_b200_ipc_close.argtypes = [vp]
     P = C.POINTER(DeviceCSR)
     L.spmv_b200_gen_laplacian2d.argtypes = [i, i, ul, P]
     L.spmv_b200_gen_stencil27.argtypes = [i, i, i, ul, P]
@@ -198,6 +204,12 @@ class Handle:
                 raise RuntimeError(last_error())
         return out
 
+    def set_y_peers(self, ptrs):
+        """Extra destinations of y (addresses); [] switches the fused scatter off."""
+        arr = (C.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
+        if lib().spmv_b200_set_y_peers(self.h, len(ptrs), arr) != 0:
+            raise ValueError("set_y_peers: at most 8 destinations")
+
     def set_stream(self, cuda_stream: int):
         lib().spmv_b200_set_stream(self.h, cuda_stream)
 
@@ -214,6 +226,41 @@ class Handle:
             self.destroy()
         except Exception:
             pass
+
+
+def device_malloc(nbytes: int) -> int:
+    p = lib().spmv_b200_malloc(nbytes)
+    if not p:
+        raise MemoryError(last_error())
+    return int(p)
+
+
+def device_free(ptr: int) -> None:
+    lib().spmv_b200_free(ptr)
+
+
+def device_memcpy(dst, src, nbytes: int, kind: int) -> None:
+    """kind 0 H2D, 1 D2H, 2 D2D (synchronous)."""
+    if lib().spmv_b200_memcpy(_addr(dst), _addr(src), nbytes, kind) != 0:
+        raise RuntimeError(last_error())
+
+
+def ipc_export(ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    if lib().spmv_b200_ipc_export(ptr, buf) != 0:
+        raise RuntimeError(last_error())
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = lib().spmv_b200_ipc_open(handle)
+    if not p:
+        raise RuntimeError(last_error())
+    return int(p)
+
+
+def ipc_close(ptr: int) -> None:
+    lib().spmv_b200_ipc_close(ptr)
 
 
 def set_option(key: str, value: int) -> None:

@@ -74,37 +74,66 @@ csr_reforder_kernel(int m, const int *__restrict__ rowptr, const int *__restrict
 // a chunk that belong to the neighbouring rows are masked out (they sit in sectors this warp fetches
 // anyway).  The last partial chunk of the whole array is read element-wise (no read past nnz).
 // ------------------------------------------------------------------------------------------------
+// one aligned 4-element chunk of a row: masked FMAs into acc
+template <typename T>
+__device__ __forceinline__ void chunk_fma(int j, int start, int end, int nnz4, const int *__restrict__ col,
+                                          const T *__restrict__ val, const T *__restrict__ x, uint64_t pl,
+                                          uint64_t pf, T &acc)
+{
+    if (j < nnz4) {
+        int c[4];
+        T v[4];
+        ldg_stream4(col + j, c, pf);
+        ldg_stream4(val + j, v, pf);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int jj = j + k;
+            if (jj >= start && jj < end) acc = fma_t(v[k], ldg_x(x + c[k], pl), acc);
+        }
+    } else {  // last partial chunk of the whole array: element-wise, never read past nnz
+        for (int k = 0; k < 4; ++k) {
+            const int jj = j + k;
+            if (jj >= start && jj < end)
+                acc = fma_t(ldg_stream(val + jj), ldg_x(x + ldg_stream(col + jj), pl), acc);
+        }
+    }
+}
+
 template <typename T, bool VEC>
 __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, int nnz4,
                                          const int *__restrict__ col, const T *__restrict__ val,
                                          const T *__restrict__ x, uint64_t pl, uint64_t pf)
 {
+    // A lane adds at most kBlock consecutive chunks into one FMA chain.  Rows on regular matrices fit one
+    // block and take the plain loop; a lane that walks a very long row alone (small tpr on a skewed
+    // matrix) folds block sums instead of piling ~sqrt(len) ulps into a single chain, which would miss
+    // the 8*eps*sum|a x| bound.  Fixed order either way: bitwise reproducible.
+    constexpr int kBlock = 64;
     T sum = 0;
     if (VEC) {
+        const int step = 4 * tpr;
+        const int first = (start & ~3) + 4 * sl;
+        if (end - first <= kBlock * step) {
 #pragma unroll 2
-        for (int j = (start & ~3) + 4 * sl; j < end; j += 4 * tpr) {
-            if (j < nnz4) {
-                int c[4];
-                T v[4];
-                ldg_stream4(col + j, c, pf);
-                ldg_stream4(val + j, v, pf);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int jj = j + k;
-                    if (jj >= start && jj < end) sum = fma_t(v[k], ldg_x(x + c[k], pl), sum);
-                }
-            } else {
-                for (int k = 0; k < 4; ++k) {
-                    const int jj = j + k;
-                    if (jj >= start && jj < end)
-                        sum = fma_t(ldg_stream(val + jj), ldg_x(x + ldg_stream(col + jj), pl), sum);
-                }
+            for (int j = first; j < end; j += step) chunk_fma<T>(j, start, end, nnz4, col, val, x, pl, pf, sum);
+        } else {
+            for (int j0 = first; j0 < end; j0 += kBlock * step) {
+                const int jend = (end - j0 > kBlock * step) ? j0 + kBlock * step : end;
+                T acc = 0;
+#pragma unroll 2
+                for (int j = j0; j < jend; j += step) chunk_fma<T>(j, start, end, nnz4, col, val, x, pl, pf, acc);
+                sum += acc;
             }
         }
     } else {
+        for (int j0 = start + sl; j0 < end; j0 += 4 * kBlock * tpr) {
+            const int jend = (end - j0 > 4 * kBlock * tpr) ? j0 + 4 * kBlock * tpr : end;
+            T acc = 0;
 #pragma unroll 4
-        for (int j = start + sl; j < end; j += tpr)
-            sum = fma_t(ldg_stream(val + j), ldg_x(x + ldg_stream(col + j), pl), sum);
+            for (int j = j0; j < jend; j += tpr)
+                acc = fma_t(ldg_stream(val + j), ldg_x(x + ldg_stream(col + j), pl), acc);
+            sum += acc;
+        }
     }
     return sum;
 }
@@ -114,10 +143,10 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
 // the OpenMP row loop becomes a grid of sub-warps, TPR lanes per row with TPR = 2^k ~ mean row
 // length / 4 chosen at create.  Fixed butterfly reduction => bitwise reproducible.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TPR, bool VEC>
+template <typename T, int TPR, bool VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__restrict__ col,
-                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y)
+                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
 {
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -129,7 +158,7 @@ csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__r
     const int end = valid ? rowptr[row + 1] : 0;
     T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
     sum = group_sum_c<T, TPR>(sum);
-    if (valid && sl == 0) stg_y(y + row, sum);
+    if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,11 +169,11 @@ csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__r
 // mean row length, so short-row and long-row regions of one matrix each get a fitting geometry.
 // Block 0 starts at row 0 (the reference leaves leading empty rows unwritten).
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+template <typename T, bool VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int *__restrict__ rowptr,
                  const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
-                 T *__restrict__ y)
+                 T *__restrict__ y, const PeerList<T> peers)
 {
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const int w = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
@@ -157,7 +186,7 @@ row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int
     const int nz = rowptr[r1] - rowptr[r0];
     const int avg = (nz + nrows - 1) / nrows;
     int tpr = 1;
-    while (tpr < 32 && 7 * tpr < avg) tpr <<= 1;
+    while (tpr < 32 && 4 * tpr < avg) tpr <<= 1;
     const int rows_per_iter = 32 / tpr;
     const int sub = lane / tpr, sl = lane & (tpr - 1);
     const int nnz4 = nnz & ~3;
@@ -168,7 +197,7 @@ row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int
         const int end = valid ? rowptr[row + 1] : 0;
         T sum = row_partial<T, VEC>(start, end, sl, tpr, nnz4, col, val, x, pl, pf);
         sum = group_sum(sum, tpr);
-        if (valid && sl == 0) stg_y(y + row, sum);
+        if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
     }
 }
 
@@ -273,14 +302,27 @@ __global__ void band_scatter_kernel(int m, int bands, int band_cols, const int *
     }
 }
 
-template <typename T>
-__global__ void band_reduce_kernel(int m, int bands, const T *__restrict__ yv, T *__restrict__ y)
+template <typename T, bool PEERS>
+__global__ void band_reduce_kernel(int m, int bands, const T *__restrict__ yv, T *__restrict__ y,
+                                   const PeerList<T> peers)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m) return;
     T s = ldg_stream(yv + r);
     for (int b = 1; b < bands; ++b) s += ldg_stream(yv + (size_t)b * m + r);
-    stg_y(y + r, s);
+    store_y<PEERS>(y, peers, r, s);
+}
+
+// y -> peers for the kernel families whose epilogue is not fused (stream-ordered after them)
+template <typename T>
+__global__ void peer_copy_kernel(long long m, const T *__restrict__ y, const PeerList<T> peers)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const T v = y[r];
+#pragma unroll
+    for (int i = 0; i < kMaxPeers; ++i)
+        if (i < peers.n) stg_y(peers.p[i] + r, v);
 }
 
 }  // namespace sb

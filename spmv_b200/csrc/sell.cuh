@@ -103,11 +103,11 @@ __global__ void sell_fill_kernel(int slices, const int *__restrict__ rowptr, con
     }
 }
 
-template <typename T>
+template <typename T, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__restrict__ full,
             const int *__restrict__ perm, const int *__restrict__ scol, const T *__restrict__ sval,
-            const T *__restrict__ x, T *__restrict__ y)
+            const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
 {
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const int s = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
@@ -155,7 +155,7 @@ sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__re
         if (++groups == 64) { sum += mid; mid = 0; groups = 0; }
     }
     sum += mid;
-    stg_y(y + perm[(long long)s * kSellC + lane], sum);
+    store_y<PEERS>(y, peers, perm[(long long)s * kSellC + lane], sum);
 }
 
 }  // namespace sb

@@ -46,7 +46,8 @@ struct Options {
     std::mutex mu;
     std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 16}, {"block_nnz", 512},
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
-                                       {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0}};
+                                       {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
+                                       {"force_merge", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -423,8 +424,11 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
         if (st->parts < 1) st->parts = 1;
         int starved = 0;
         if (!build_splitter(st, st->a_m, st->a_rowptr, st->parts, &st->splitter, &starved)) return false;
-        // Balanced2 was asked for, or a row is long enough to starve a row block: merge-path
-        if (method == Method_Balanced2 || starved) return build_tiles(st, /*merge=*/true);
+        // The reference's rule (parallel_balanced2_spmv.c:87-94), applied to the GPU's own partition: a
+        // starved block (some row spans more than a block) => merge-path; otherwise both methods run the
+        // row-block kernel ("Balanced2 demoted to Balanced").  Option force_merge=1 keeps merge-path for
+        // every Method_Balanced2 handle.
+        if (starved || (method == Method_Balanced2 && opt("force_merge") != 0)) return build_tiles(st, /*merge=*/true);
         st->kernel = SPMV_B200_KERNEL_ROW_BLOCKS;
         return true;
     }
@@ -524,11 +528,14 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
 // launch dispatch (a3: the reference's spmv_functions[] table, common.c:85-94)
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool VEC>
-static void launch_vector(DeviceState *st, int tpr, const T *x, T *y)
+static void launch_vector(DeviceState *st, int tpr, const T *x, T *y, const PeerList<T> &peers)
 {
     const int m = st->a_m;
     const int grid = blocks_for((long long)m * tpr);
-#define SB_CASE(N) case N: csr_vector_kernel<T, N, VEC><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y); break;
+#define SB_CASE(N) case N: \
+        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        break;
     switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
 #undef SB_CASE
     count_launch();
@@ -563,8 +570,16 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     }
     // the active view: the CSR itself, or its band-major copy writing the virtual y
     const int m = st->a_m;
-    T *y = st->x_bands > 1 ? (T *)st->v_y : y_out;
+    const bool banded = st->x_bands > 1;
+    T *y = banded ? (T *)st->v_y : y_out;
     const T *val = (const T *)st->a_val;
+    // extra y destinations (fused all-gather): written by whichever kernel produces the FINAL y
+    PeerList<T> peers, none;
+    none.n = 0;
+    peers.n = st->n_peers;
+    for (int i = 0; i < kMaxPeers; ++i) { peers.p[i] = (T *)st->peers[i]; none.p[i] = nullptr; }
+    const PeerList<T> &direct = banded ? none : peers;  // kernels write virtual y when banded
+    bool scattered = peers.n == 0;
     switch (st->kernel) {
     case SPMV_B200_KERNEL_CSR_REFORDER: {
         constexpr int L = sizeof(T) == 8 ? 4 : 8;
@@ -573,12 +588,16 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         break;
     }
     case SPMV_B200_KERNEL_CSR_VECTOR:
-        if (st->vec_ok) launch_vector<T, true>(st, st->tpr, x, y); else launch_vector<T, false>(st, st->tpr, x, y);
+        if (st->vec_ok) launch_vector<T, true>(st, st->tpr, x, y, direct); else launch_vector<T, false>(st, st->tpr, x, y, direct);
+        scattered = scattered || !banded;
         break;
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
         const int grid = blocks_for((long long)st->parts * 32);
-        if (st->vec_ok) row_block_kernel<T, true><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y);
-        else row_block_kernel<T, false><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y);
+#define SB_RB(V, P) row_block_kernel<T, V, P><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y, direct)
+        if (st->vec_ok) { if (direct.n > 0) SB_RB(true, true); else SB_RB(true, false); }
+        else { if (direct.n > 0) SB_RB(false, true); else SB_RB(false, false); }
+#undef SB_RB
+        scattered = scattered || !banded;
         count_launch();
         break;
     }
@@ -602,8 +621,14 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     }
     case SPMV_B200_KERNEL_SELL: {
         if (st->slices > 0) {
-            sell_kernel<T><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
-                st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y);
+            const PeerList<T> &sp = (st->banner == m) ? direct : none;
+            if (sp.n > 0)
+                sell_kernel<T, true><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
+                    st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp);
+            else
+                sell_kernel<T, false><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
+                    st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp);
+            scattered = scattered || (!banded && st->banner == m);
             count_launch();
         }
         if (st->banner < m) {
@@ -637,8 +662,14 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         set_error("handle has no kernel (%d)", st->kernel);
         return false;
     }
-    if (st->x_bands > 1) {
-        band_reduce_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out);
+    if (banded) {
+        if (peers.n > 0) band_reduce_kernel<T, true><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
+        else band_reduce_kernel<T, false><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
+        scattered = true;
+        count_launch();
+    }
+    if (!scattered) {  // kernel family without a fused epilogue: one stream-ordered copy to the peers
+        peer_copy_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out, peers);
         count_launch();
     }
     return SB_CUDA(cudaGetLastError());
@@ -792,6 +823,41 @@ void spmv_b200_sync(spmv_Handle_t handle)
         DeviceGuard g(st->device);
         SB_CUDA(cudaStreamSynchronize(st->stream));
     }
+}
+
+int spmv_b200_set_y_peers(spmv_Handle_t handle, int count, void *const *device_ptrs)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || count < 0 || count > kMaxPeers || (count > 0 && !device_ptrs)) return -1;
+    st->n_peers = count;
+    for (int i = 0; i < kMaxPeers; ++i) st->peers[i] = i < count ? device_ptrs[i] : nullptr;
+    return 0;
+}
+
+int spmv_b200_ipc_export(const void *device_ptr, void *handle_out_64)
+{
+    if (!device_ptr || !handle_out_64) return -1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (!SB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)))) return -1;
+    memcpy(handle_out_64, &h, sizeof(h));
+    return 0;
+}
+
+void *spmv_b200_ipc_open(const void *handle_64)
+{
+    if (!handle_64) return nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, sizeof(h));
+    void *p = nullptr;
+    if (!SB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess))) return nullptr;
+    return p;
+}
+
+int spmv_b200_ipc_close(void *opened_ptr)
+{
+    if (!opened_ptr) return -1;
+    return SB_CUDA(cudaIpcCloseMemHandle(opened_ptr)) ? 0 : -1;
 }
 
 int spmv_b200_set_option(const char *key, long long value)

@@ -98,3 +98,80 @@ class PowerMethod:
             t_spmv = sum(e[0].elapsed_time(e[1]) for e in ev)
             t_comm = sum(e[1].elapsed_time(e[2]) for e in ev)
         return self.x[cur], t_spmv / max(iters, 1), t_comm / max(iters, 1)
+
+
+class FusedPowerMethod:
+    """x <- A x with the all-gather fused into the SpMV: the kernel that produces y stores every value into
+    this rank's next x AND, over NVLink peer mappings (CUDA IPC), into every other rank's next x at the
+    same row offset (spmv_b200_set_y_peers).  No collective moves data; one 1-element all-reduce per
+    iteration orders the ranks before the next x is read.
+
+    `handle` is this rank's spmv_b200.api.Handle; `splitter` the global row partition; `x0` a CUDA tensor.
+    The two x buffers are plain cudaMalloc allocations (IPC-exportable), not torch storage.
+    """
+
+    def __init__(self, handle, splitter: Sequence[int], x0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.h = torch, dist, group, handle
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.splitter = [int(v) for v in splitter]
+        self.n, self.item = x0.numel(), x0.element_size()
+        assert self.splitter[-1] == self.n and len(self.splitter) == self.world + 1
+        nbytes = self.n * self.item
+        self.buf = [api.device_malloc(nbytes), api.device_malloc(nbytes)]
+        api.device_memcpy(self.buf[0], x0, nbytes, 2)
+        self.opened = []
+        mine = [api.ipc_export(b) for b in self.buf]
+        if self.world > 1:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+        else:
+            everyone = [mine]
+        lo = self.splitter[self.rank] * self.item
+        self.peer_dst = [[], []]  # per buffer parity: where my slice starts inside every OTHER rank's buffer
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            for parity in (0, 1):
+                base = api.ipc_open(everyone[q][parity])
+                self.opened.append(base)
+                self.peer_dst[parity].append(base + lo)
+        self.flag = torch.zeros(1, device=x0.device)
+        self.dtype, self.device = x0.dtype, x0.device
+
+    def run(self, iters: int):
+        torch, dist = self.torch, self.dist
+        lo = self.splitter[self.rank] * self.item
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+        cur = 0
+        for it in range(iters):
+            nxt = 1 - cur
+            self.h.set_y_peers(self.peer_dst[nxt])
+            ev[it][0].record()
+            self.h.spmv(self.buf[cur], self.buf[nxt] + lo)  # local slice + peer stores in one kernel
+            ev[it][1].record()
+            if self.world > 1:
+                dist.all_reduce(self.flag, group=self.group)  # ordering only: everyone's stores have landed
+            ev[it][2].record()
+            cur = nxt
+        torch.cuda.synchronize()
+        self.h.set_y_peers([])
+        self.cur = cur
+        t_spmv = sum(e[0].elapsed_time(e[1]) for e in ev) / max(iters, 1)
+        t_sync = sum(e[1].elapsed_time(e[2]) for e in ev) / max(iters, 1)
+        return t_spmv, t_sync
+
+    def result(self):
+        x = self.torch.empty(self.n, dtype=self.dtype, device=self.device)
+        api.device_memcpy(x, self.buf[self.cur], self.n * self.item, 2)
+        return x
+
+    def close(self):
+        for p in self.opened:
+            api.ipc_close(p)
+        self.opened = []
+        for b in self.buf:
+            api.device_free(b)
+        self.buf = []

@@ -72,6 +72,35 @@ def test_all_methods_match_reference_serial(libpath, port, serial_ref, name, dt)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+def test_merge_path_forced_on_every_case(libpath, port, serial_ref, dt):
+    """Method_Balanced2 normally runs merge-path only when a row starves a row block (the reference's
+    Balanced2 -> Balanced rule); force it everywhere so the kernel is covered on regular matrices too."""
+    api.set_option("force_merge", 1)
+    try:
+        for name, make in CASES.items():
+            a = make().astype(dt)
+            x = M.make_x(a.n, 4321, dt)
+            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Balanced2)
+            assert h.kernel in ("merge_path", "none"), name
+            y = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y)
+            check_y(port, serial_ref, a, x, y, api.Method_Balanced2, f"force_merge/{name}")
+            h.destroy()
+    finally:
+        api.set_option("force_merge", 0)
+
+
+def test_balanced2_follows_reference_demotion(libpath):
+    """No starved block -> row-block kernel; a long row -> merge-path (for Balanced and Balanced2 alike)."""
+    for name, want in (("uni32", "row_blocks"), ("lap48", "row_blocks"), ("hub", "merge_path"), ("one_long_row", "merge_path")):
+        a = CASES[name]()
+        for method in (api.Method_Balanced, api.Method_Balanced2):
+            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+            assert h.kernel == want, (name, method, h.kernel)
+            h.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
 def test_signed_data_with_cancellation(libpath, port, serial_ref, dt):
     """Mixed-sign values and x: the bound is relative to sum|a x|, not to |y|."""
     rng = np.random.default_rng(17)
@@ -178,4 +207,38 @@ def test_band_major_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
             y2 = np.full(a.m, np.nan, dtype=dt)
             h.spmv(x, y2)
             assert bits_equal(y, y2), tag
+            h.destroy()
+
+
+def test_fused_peer_scatter_single_gpu_emulation(libpath, port, serial_ref):
+    """spmv_b200_set_y_peers: every y value also lands in the extra destinations (here: local buffers that
+    stand in for the peers' next-x slices), for the fused kernels and for the copy fallback alike."""
+    import torch
+    dev = torch.device("cuda:0")
+    for name, bands in (("uni32", 0), ("skew", 0), ("hub", 0), ("uni32", 3), ("lap48", 0)):
+        a = CASES[name]()
+        x = torch.from_numpy(M.make_x(a.n, 3, np.float64)).to(dev)
+        for method in METHODS:
+            api.set_option("x_bands", bands)
+            try:
+                h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+            finally:
+                api.set_option("x_bands", 0)
+            y = torch.full((a.m,), float("nan"), dtype=torch.float64, device=dev)
+            big = torch.full((3, a.m + 10), float("nan"), dtype=torch.float64, device=dev)
+            peers = [big[i, 5:].data_ptr() for i in range(3)]  # slices at a row offset inside larger buffers
+            h.set_y_peers(peers)
+            h.spmv(x, y)
+            h.sync()
+            yh = y.cpu().numpy()
+            check_y(port, serial_ref, a, x.cpu().numpy(), yh, method, f"peers/{name}/{api.METHOD_NAMES[method]}")
+            for i in range(3):
+                assert bits_equal(big[i, 5:5 + a.m].cpu().numpy(), yh), (name, method, i)
+                assert torch.isnan(big[i, :5]).all() and torch.isnan(big[i, 5 + a.m:]).all()
+            h.set_y_peers([])
+            y2 = torch.zeros_like(y)
+            big.fill_(float("nan"))
+            h.spmv(x, y2)
+            h.sync()
+            assert torch.isnan(big).all() and bits_equal(y2.cpu().numpy(), yh)
             h.destroy()

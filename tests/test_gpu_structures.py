@@ -33,7 +33,10 @@ def test_tile_rows_and_merge_coords(libpath, port, name):
     want = [port.lib.oracle_right_boundary(a.rowptr, min(t * per, a.nnz), a.m + 1) - 1 for t in range(tiles + 1)]
     assert np.array_equal(tr, np.array(want, np.int32))
     h.destroy()
+    api.set_option("force_merge", 1)
     h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Balanced2)
+    api.set_option("force_merge", 0)
+    assert h.kernel == "merge_path"
     tiles = h.info("tiles")
     mc = h.structure("merge_coords", np.int32).reshape(-1, 2)
     d = np.minimum(np.arange(tiles + 1, dtype=np.int64) * per, a.m + a.nnz)
