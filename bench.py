@@ -289,6 +289,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod

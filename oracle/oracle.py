@@ -35,6 +35,11 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", HERE, "port"], check=True)
     if ref:
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", HERE, "drivers"], check=True)
+
+
+DRIVER_REF = os.path.join(HERE, "_ref", "test_spmv_ref")
+DRIVER_B200 = os.path.join(HERE, "_ref", "test_spmv_b200")
 
 
 def have_reference() -> bool:

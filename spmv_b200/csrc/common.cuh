@@ -168,20 +168,25 @@ __device__ __forceinline__ double ldg_stream(const double *p, uint64_t pol)
 }
 
 // ---- 4-element chunk loads (element index multiple of 4; base 32-byte aligned) ----
+// L2 evict-first, but ALLOWED to allocate in L1: neighbouring rows share chunk sectors, and letting the
+// line live in L1 for a few hundred cycles saves the re-fetch from L2 (measured +1-2 % on C1/C2/C4).
 __device__ __forceinline__ void ldg_stream4(const int *p, int (&r)[4], uint64_t pol)
 {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p), "l"(pol));
 }
 __device__ __forceinline__ void ldg_stream4(const float *p, float (&r)[4], uint64_t pol)
 {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+
                  : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(p), "l"(pol));
 }
 __device__ __forceinline__ void ldg_stream4(const double *p, double (&r)[4], uint64_t)
 {
     unsigned long long a, b, c, d;  // one 256-bit load, L2 evict-first encoded in the instruction
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+
                  : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     r[0] = __longlong_as_double((long long)a);
     r[1] = __longlong_as_double((long long)b);
