@@ -42,7 +42,9 @@ struct DeviceState {
     int kernel = SPMV_B200_KERNEL_NONE;
     bool ok = false;                // false => spmv() is a no-op
     bool has_empty_rows = false;
-    bool vec_ok = true;             // ColIdx / Val 32-byte aligned: 128/256-bit loads allowed
+    bool aligned = true;            // ColIdx / Val of the active view are 32-byte aligned
+    int rb_mode = 1;                // the same choice for the row-block kernel
+    int load_mode = 1;              // CSR kernels: 1 = aligned 128/256-bit chunk loads, 2 = scalar via L1, 0 = scalar no-L1
     long long dev_l2 = 0, dev_persist_max = 0, dev_window_max = 0, cur_persist = 0, cur_fetch = 0;
     bool x_window = false;
     const void *window_base = nullptr;
@@ -85,6 +87,12 @@ struct DeviceState {
     int *sell_perm = nullptr, *sell_width = nullptr, *sell_full = nullptr, *sell_col = nullptr;
     long long *sell_slice_ptr = nullptr;
     void *sell_val = nullptr;
+    // long rows / row tails left over by the main kernel of Method_Parallel and Method_SellCSigma (long_rows.cuh)
+    int long_thr = 0x7fffffff;      // CSR-vector kernels skip rows longer than this
+    int lr_rows = 0, lr_segs = 0;
+    bool lr_accumulate = false;     // true: the main kernel already wrote the head of the row (SELL)
+    int *lr_row = nullptr, *lr_start = nullptr, *lr_seg_ptr = nullptr, *lr_seg_row = nullptr;
+    void *lr_partial = nullptr;
     // Method_CSR5SPMV (omega = 32)
     int c5_sigma = 0, c5_p = 0, c5_bit_y = 0, c5_bit_ss = 0, c5_num_offsets = 0, c5_tail_start = 0;
     uint32_t *c5_tile_ptr = nullptr, *c5_tile_desc = nullptr;
@@ -164,6 +172,26 @@ __device__ __forceinline__ double ldg_stream(const double *p, uint64_t pol)
 {
     double r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
+// ---- scalar matrix-stream loads that DO allocate in L1 (L2 evict-first) ----
+__device__ __forceinline__ int ldg_cached(const int *p, uint64_t pol)
+{
+    int r;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_cached(const float *p, uint64_t pol)
+{
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ldg_cached(const double *p, uint64_t pol)
+{
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
     return r;
 }
 

@@ -99,7 +99,10 @@ __device__ __forceinline__ void chunk_fma(int j, int start, int end, int nnz4, c
     }
 }
 
-template <typename T, bool VEC>
+// MODE 1: aligned 4-element chunks (128/256-bit loads).  MODE 0: scalar loads that bypass L1.  MODE 2: scalar
+// loads that allocate in L1 (L2 evict-first): the tpr lanes of a row walk it with stride tpr, so one 32-byte
+// sector serves several consecutive iterations of the same warp and should be fetched from L2 only once.
+template <typename T, int MODE>
 __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, int nnz4,
                                          const int *__restrict__ col, const T *__restrict__ val,
                                          const T *__restrict__ x, uint64_t pl, uint64_t pf)
@@ -110,7 +113,7 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
     // the 8*eps*sum|a x| bound.  Fixed order either way: bitwise reproducible.
     constexpr int kBlock = 64;
     T sum = 0;
-    if (VEC) {
+    if (MODE == 1) {
         const int step = 4 * tpr;
         const int first = (start & ~3) + 4 * sl;
         if (end - first <= kBlock * step) {
@@ -122,6 +125,21 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
                 T acc = 0;
 #pragma unroll 2
                 for (int j = j0; j < jend; j += step) chunk_fma<T>(j, start, end, nnz4, col, val, x, pl, pf, acc);
+                sum += acc;
+            }
+        }
+    } else if (MODE == 2) {
+        if (end - start <= 4 * kBlock * tpr) {
+#pragma unroll 4
+            for (int j = start + sl; j < end; j += tpr)
+                sum = fma_t(ldg_cached(val + j, pf), ldg_x(x + ldg_cached(col + j, pf), pl), sum);
+        } else {
+            for (int j0 = start + sl; j0 < end; j0 += 4 * kBlock * tpr) {
+                const int jend = (end - j0 > 4 * kBlock * tpr) ? j0 + 4 * kBlock * tpr : end;
+                T acc = 0;
+#pragma unroll 4
+                for (int j = j0; j < jend; j += tpr)
+                    acc = fma_t(ldg_cached(val + j, pf), ldg_x(x + ldg_cached(col + j, pf), pl), acc);
                 sum += acc;
             }
         }
@@ -143,19 +161,20 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
 // the OpenMP row loop becomes a grid of sub-warps, TPR lanes per row with TPR = 2^k ~ mean row
 // length / 4 chosen at create.  Fixed butterfly reduction => bitwise reproducible.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TPR, bool VEC, bool PEERS>
+template <typename T, int TPR, int VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
-csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__restrict__ col,
+csr_vector_kernel(int m, int nnz, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
                   const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
 {
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long row_l = gt / TPR;
     const int sl = threadIdx.x & (TPR - 1);
-    const bool valid = row_l < m;
+    bool valid = row_l < m;
     const int row = valid ? (int)row_l : 0;
-    const int start = valid ? rowptr[row] : 0;
-    const int end = valid ? rowptr[row + 1] : 0;
+    int start = valid ? rowptr[row] : 0;
+    int end = valid ? rowptr[row + 1] : 0;
+    if (end - start > long_thr) { valid = false; end = start; }  // hub row: left to the long-row path
     T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
     sum = group_sum_c<T, TPR>(sum);
     if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
@@ -169,7 +188,7 @@ csr_vector_kernel(int m, int nnz, const int *__restrict__ rowptr, const int *__r
 // mean row length, so short-row and long-row regions of one matrix each get a fitting geometry.
 // Block 0 starts at row 0 (the reference leaves leading empty rows unwritten).
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool VEC, bool PEERS>
+template <typename T, int VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int *__restrict__ rowptr,
                  const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,

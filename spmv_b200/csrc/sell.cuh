@@ -54,10 +54,16 @@ sell_sort_kernel(int sigma, int pow2, const int *__restrict__ rowptr, int *__res
         perm[row_base + i] = (int)(row_base + (unsigned)(s_key[i] & 0xffffffffu));
 }
 
-// per slice: width (max row length), full (min row length), padded element count
-__global__ void sell_width_kernel(int slices, const int *__restrict__ rowptr, const int *__restrict__ perm,
+// per slice: width, full (min row length), padded element count.  width = the longest row of the slice, as in
+// the reference (ld, sell_C_Sigma_spmv.c:84-92) -- unless `cap` is set and the slice would be mostly padding
+// (32*max > 2*sum of lengths: a hub row among short ones).  Then the width is the row length l_i that
+// minimises  32*l_i + 2*overflow(l_i) + 64*rows_over(l_i)  and the entries beyond it (`overflow`) are left
+// to the long-row path (long_rows.cuh).  The rows of a slice arrive sorted by length, so lane i holds l_i.
+// In any case a slice is at most `cap` columns wide: one warp walks a slice column by column, and a slice of
+// 10^5 columns would run for milliseconds after the rest of the grid has finished.
+__global__ void sell_width_kernel(int slices, int cap, const int *__restrict__ rowptr, const int *__restrict__ perm,
                                   int *__restrict__ width, int *__restrict__ full,
-                                  long long *__restrict__ count)
+                                  long long *__restrict__ count, int *__restrict__ covered)
 {
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -65,15 +71,42 @@ __global__ void sell_width_kernel(int slices, const int *__restrict__ rowptr, co
     const int r = perm[(long long)s * kSellC + lane];
     const int len = rowptr[r + 1] - rowptr[r];
     int mx = len, mn = len;
+    long long total = len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mx = max(mx, __shfl_xor_sync(kFull, mx, o));
         mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+        total += __shfl_xor_sync(kFull, total, o);
     }
+    int w = mx;
+    if (cap > 0 && (long long)kSellC * mx > 2 * total) {
+        // suffix sum of the lengths after lane i (lengths ascend with the lane)
+        long long incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const long long after = total - incl;  // sum of l_j, j > lane
+        const long long over = after - (long long)(31 - lane) * len;
+        int rows_over = 0;  // rows strictly longer than this lane's
+        for (int j = 0; j < 32; ++j) rows_over += __shfl_sync(kFull, len, j) > len;
+        long long cost = (long long)kSellC * len + 2 * over + 64LL * rows_over;
+        int best = len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // min cost, ties -> the larger width
+            const long long c2 = __shfl_xor_sync(kFull, cost, o);
+            const int b2 = __shfl_xor_sync(kFull, best, o);
+            if (c2 < cost || (c2 == cost && b2 > best)) { cost = c2; best = b2; }
+        }
+        w = best;
+    }
+    if (cap > 0 && w > cap) w = cap;
+    if (covered) covered[r] = min(len, w);
     if (lane == 0) {
-        width[s] = mx;
-        full[s] = mn;
-        count[s] = (long long)mx * kSellC;
+        width[s] = w;
+        full[s] = min(mn, w);
+        count[s] = (long long)w * kSellC;
     }
 }
 

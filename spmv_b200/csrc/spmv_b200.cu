@@ -15,6 +15,7 @@
 #include "tile_kernels.cuh"
 #include "sell.cuh"
 #include "csr5.cuh"
+#include "long_rows.cuh"
 
 namespace sb {
 
@@ -47,7 +48,8 @@ struct Options {
     std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 16}, {"block_nnz", 512},
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
-                                       {"force_merge", 0}};
+                                       {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
+                                       {"long_thr", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -148,6 +150,11 @@ static void free_layouts(DeviceState *st)
     dfree(st->c5_off); st->c5_off = nullptr;
     dfree(st->c5_col); st->c5_col = nullptr;
     dfree(st->c5_val); st->c5_val = nullptr;
+    dfree(st->lr_row); st->lr_row = nullptr;
+    dfree(st->lr_start); st->lr_start = nullptr;
+    dfree(st->lr_seg_ptr); st->lr_seg_ptr = nullptr;
+    dfree(st->lr_seg_row); st->lr_seg_row = nullptr;
+    dfree(st->lr_partial); st->lr_partial = nullptr;
     dfree(st->x_stage); st->x_stage = nullptr;
     dfree(st->y_stage); st->y_stage = nullptr;
 }
@@ -188,6 +195,20 @@ static void apply_device_limits(DeviceState *st)
     st->x_window = opt("x_window") != 0;
 }
 
+// How the CSR kernels read ColIdx / Val.  Option "vec": -1 = automatic from the locality probe, 1 = aligned
+// 4-element chunks (128/256-bit loads; needs 32-byte aligned arrays), 2 = scalar loads through L1, 0 = scalar
+// loads bypassing L1.
+static void resolve_load_mode(DeviceState *st)
+{
+    long long mode = opt("vec");
+    const bool forced = mode >= 0 && mode <= 2;
+    if (!forced) mode = (st->far_fraction > 0.25) ? 1 : 2;
+    if (mode == 1 && !st->aligned) mode = 2;
+    st->load_mode = (int)mode;
+    // the row-block kernel (run-time lanes per row) measured faster with chunk loads on every matrix
+    st->rb_mode = forced ? (int)mode : (st->aligned ? 1 : 2);
+}
+
 static int pick_tpr(long long nnz, int m)
 {
     const long long forced = opt("tpr");
@@ -209,25 +230,31 @@ static bool build_band_major(DeviceState *st)
     long long bands = opt("x_bands");  // 0 = automatic, 1 = off, >= 2 forced
     const double xbytes = (double)st->n * st->vsize;
     const double usable = st->dev_l2 > 0 ? 0.5 * (double)st->dev_l2 : 63.0 * 1048576.0;  // random-access reach
+    {
+        // locality probe: the share of entries further than 1/8 of the L2 reach from the (scaled) diagonal.
+        // It decides two things: whether banding pays (below) and how the CSR kernels read the matrix
+        // streams -- gather-dominated matrices are bound by L2 requests and want the fewest, widest stream
+        // loads (128/256-bit chunks); diagonal-local ones are bound by DRAM and run best with plain scalar
+        // loads through L1 (measured: C1 0.50 -> 0.62, C4 0.69 -> 0.76 of the HBM peak; C2 0.39 -> 0.36).
+        unsigned long long *far = nullptr, h_far = 0;
+        if (!dmalloc(&far, 1)) return false;
+        SB_TRY(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
+        const int halfwidth = (int)(0.125 * usable / st->vsize);
+        band_locality_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(
+            st->m, (double)st->n / st->m, halfwidth, st->rowptr, st->col, far);
+        SB_TRY(cudaMemcpyAsync(&h_far, far, sizeof(h_far), cudaMemcpyDeviceToHost, st->stream));
+        SB_TRY(cudaStreamSynchronize(st->stream));
+        dfree(far);
+        st->far_fraction = (double)h_far / (double)st->nnz;
+        resolve_load_mode(st);
+    }
     if (bands == 0) {
         bands = 1;
         if (xbytes > 0.9 * usable) {
             long long k = (long long)ceil(xbytes / (0.75 * usable));
-            // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save
-            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0) {
-                // ... and band only when the accesses are NOT already diagonal-local
-                unsigned long long *far = nullptr, h_far = 0;
-                if (!dmalloc(&far, 1)) return false;
-                SB_TRY(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
-                const int halfwidth = (int)(0.125 * usable / st->vsize);
-                band_locality_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(
-                    st->m, (double)st->n / st->m, halfwidth, st->rowptr, st->col, far);
-                SB_TRY(cudaMemcpyAsync(&h_far, far, sizeof(h_far), cudaMemcpyDeviceToHost, st->stream));
-                SB_TRY(cudaStreamSynchronize(st->stream));
-                dfree(far);
-                st->far_fraction = (double)h_far / (double)st->nnz;
-                if (st->far_fraction > 0.25) bands = k;
-            }
+            // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save,
+            // and banding only pays when the accesses are NOT already diagonal-local
+            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0 && st->far_fraction > 0.25) bands = k;
         }
     }
     if (bands <= 1) return true;
@@ -253,7 +280,8 @@ static bool build_band_major(DeviceState *st)
     st->x_bands = K;
     st->band_cols = band_cols;
     st->a_m = (int)vm; st->a_rowptr = st->v_rowptr; st->a_col = st->v_col; st->a_val = st->v_val;
-    st->vec_ok = true;
+    st->aligned = true;  // the band copy is our own 256-byte aligned allocation
+    resolve_load_mode(st);
     return true;
 }
 
@@ -273,6 +301,54 @@ static bool build_splitter(DeviceState *st, int m, const int *rowptr, int parts,
         if (!ok) return false;
     }
     return true;
+}
+
+// Segment list for the entries the main kernel does not cover: covered[r] leading entries of row r are done
+// by the main kernel, the rest by long_seg_kernel / long_final_kernel (long_rows.cuh).  Frees `covered`.
+static bool build_long_rows(DeviceState *st, int *covered, bool accumulate)
+{
+    const int m = st->a_m;
+    int *cnt_r = nullptr, *cnt_s = nullptr, *scan_r = nullptr, *scan_s = nullptr;
+    bool ok = dmalloc(&cnt_r, (size_t)m + 1) && dmalloc(&cnt_s, (size_t)m + 1) && dmalloc(&scan_r, (size_t)m + 1) &&
+              dmalloc(&scan_s, (size_t)m + 1);
+    if (ok) {
+        long_count_kernel<<<blocks_for((long long)m + 1), kThreads, 0, st->stream>>>(m, st->a_rowptr, covered, cnt_r, cnt_s);
+        ok = SB_CUDA(cudaGetLastError()) && exclusive_scan(cnt_r, scan_r, m + 1, st->stream) &&
+             exclusive_scan(cnt_s, scan_s, m + 1, st->stream);
+    }
+    int totals[2] = {0, 0};
+    if (ok) ok = SB_CUDA(cudaMemcpy(&totals[0], scan_r + m, sizeof(int), cudaMemcpyDeviceToHost)) &&
+                 SB_CUDA(cudaMemcpy(&totals[1], scan_s + m, sizeof(int), cudaMemcpyDeviceToHost));
+    st->lr_rows = totals[0];
+    st->lr_segs = totals[1];
+    st->lr_accumulate = accumulate;
+    if (ok && st->lr_rows > 0) {
+        ok = dmalloc(&st->lr_row, (size_t)st->lr_rows) && dmalloc(&st->lr_start, (size_t)st->lr_rows) &&
+             dmalloc(&st->lr_seg_ptr, (size_t)st->lr_rows + 1) && dmalloc(&st->lr_seg_row, (size_t)st->lr_segs) &&
+             SB_CUDA(cudaMalloc(&st->lr_partial, (size_t)st->lr_segs * st->vsize));
+        if (ok) {
+            long_fill_kernel<<<blocks_for((long long)m + 1), kThreads, 0, st->stream>>>(
+                m, st->a_rowptr, covered, scan_r, scan_s, st->lr_row, st->lr_start, st->lr_seg_ptr, st->lr_seg_row);
+            ok = SB_CUDA(cudaGetLastError()) && SB_CUDA(cudaStreamSynchronize(st->stream));
+        }
+    }
+    dfree(cnt_r); dfree(cnt_s); dfree(scan_r); dfree(scan_s); dfree(covered);
+    return ok;
+}
+
+// Method_Parallel: rows longer than ~256 entries per lane would keep one lane group busy long after the rest
+// of the grid has drained; they go to the long-row path as a whole.
+static bool build_long_rows_threshold(DeviceState *st, int tpr)
+{
+    long long thr = opt("long_thr");  // 0 = automatic, < 0 = off
+    if (thr < 0) { st->long_thr = 0x7fffffff; return true; }
+    if (thr == 0) { thr = 256LL * tpr; if (thr < 512) thr = 512; if (thr > 4096) thr = 4096; }
+    st->long_thr = (int)thr;
+    int *covered = nullptr;
+    if (!dmalloc(&covered, (size_t)st->a_m + 1)) return false;
+    long_cover_threshold_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, 0, st->long_thr, st->a_rowptr, covered);
+    SB_TRY(cudaGetLastError());
+    return build_long_rows(st, covered, /*accumulate=*/false);
 }
 
 static bool build_tiles(DeviceState *st, bool merge)
@@ -313,7 +389,18 @@ static bool build_sell(DeviceState *st)
     st->slices = st->banner / kSellC;
     st->tpr = pick_tpr(st->nnz, st->a_m);  // for the CSR tail rows [banner, m)
     st->kernel = SPMV_B200_KERNEL_SELL;
-    if (st->banner == 0) return true;
+    // covered[r]: entries of row r stored in its slice (sell_width_kernel); tail rows [banner, m) stay CSR,
+    // except hub rows, which csr_tail_kernel zeroes and the long-row path then adds as a whole
+    long long cap_opt = opt("sell_cap");  // 0 = off (the reference's widths), else the widest slice allowed
+    const int cap = cap_opt <= 0 ? 0 : (int)(cap_opt < 32 ? 32 : (cap_opt > (1 << 20) ? (1 << 20) : cap_opt));
+    int *covered = nullptr;
+    if (cap) {
+        if (!dmalloc(&covered, (size_t)st->a_m + 1)) return false;
+        st->long_thr = 4096;
+        long_cover_threshold_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, st->banner, st->long_thr, st->a_rowptr, covered);
+        SB_TRY(cudaGetLastError());
+    }
+    if (st->banner == 0) return cap ? build_long_rows(st, covered, /*accumulate=*/true) : true;
     int pow2 = 1;
     while (pow2 < st->sigma) pow2 <<= 1;
     if (!dmalloc(&st->sell_perm, (size_t)st->banner)) return false;
@@ -326,8 +413,9 @@ static bool build_sell(DeviceState *st)
         return false;
     SB_TRY(cudaMemsetAsync(count, 0, ((size_t)st->slices + 1) * sizeof(long long), st->stream));
     sell_width_kernel<<<blocks_for((long long)st->slices * 32), kThreads, 0, st->stream>>>(
-        st->slices, st->a_rowptr, st->sell_perm, st->sell_width, st->sell_full, count);
+        st->slices, cap, st->a_rowptr, st->sell_perm, st->sell_width, st->sell_full, count, covered);
     SB_TRY(cudaGetLastError());
+    if (cap && !build_long_rows(st, covered, /*accumulate=*/true)) return false;
     const bool ok = exclusive_scan(count, st->sell_slice_ptr, st->slices + 1, st->stream);
     dfree(count);
     if (!ok) return false;
@@ -408,7 +496,7 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
     case Method_Parallel:
         st->tpr = pick_tpr(st->nnz, st->a_m);
         st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
-        return true;
+        return build_long_rows_threshold(st, st->tpr);
     case Method_Balanced:
     case Method_Balanced2: {
         // mirror of the reference's demotion / promotion rule with the CALLER's nthreads (a10,
@@ -496,7 +584,8 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
             SB_TRY(cudaMemcpy(st->val, Val, (size_t)st->nnz * st->vsize, cudaMemcpyHostToDevice));
         }
     }
-    st->vec_ok = (((uintptr_t)st->col | (uintptr_t)st->val) & 31u) == 0;
+    st->aligned = (((uintptr_t)st->col | (uintptr_t)st->val) & 31u) == 0;
+    resolve_load_mode(st);
 
     st->a_m = st->m; st->a_rowptr = st->rowptr; st->a_col = st->col; st->a_val = st->val;
     if (method != Method_Serial) {  // Method_Serial keeps the reference's exact summation order: never banded
@@ -527,14 +616,14 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
 // ------------------------------------------------------------------------------------------------
 // launch dispatch (a3: the reference's spmv_functions[] table, common.c:85-94)
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+template <typename T, int VEC>
 static void launch_vector(DeviceState *st, int tpr, const T *x, T *y, const PeerList<T> &peers)
 {
     const int m = st->a_m;
     const int grid = blocks_for((long long)m * tpr);
 #define SB_CASE(N) case N: \
-        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
-        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
         break;
     switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
 #undef SB_CASE
@@ -544,7 +633,7 @@ static void launch_vector(DeviceState *st, int tpr, const T *x, T *y, const Peer
 // CSR-vector over rows [row0, m) only (the CSR tail of SELL)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-csr_tail_kernel(int row0, int m, const int *__restrict__ rowptr, const int *__restrict__ col,
+csr_tail_kernel(int row0, int m, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
                 const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y)
 {
     const uint64_t pl = policy_evict_last();
@@ -552,8 +641,11 @@ csr_tail_kernel(int row0, int m, const int *__restrict__ rowptr, const int *__re
     const int lane = threadIdx.x & 31;
     if (row0 + w >= m) return;
     const int row = (int)(row0 + w);
+    const int start = rowptr[row];
+    int end = rowptr[row + 1];
+    if (end - start > long_thr) end = start;  // hub row: y = 0 here, the long-row path adds the whole row
     T sum = 0;
-    for (int j = rowptr[row] + lane; j < rowptr[row + 1]; j += 32) sum = fma_t(val[j], ldg_x(x + col[j], pl), sum);
+    for (int j = start + lane; j < end; j += 32) sum = fma_t(val[j], ldg_x(x + col[j], pl), sum);
     sum = group_sum_c<T, 32>(sum);
     if (lane == 0) y[row] = sum;
 }
@@ -588,14 +680,17 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         break;
     }
     case SPMV_B200_KERNEL_CSR_VECTOR:
-        if (st->vec_ok) launch_vector<T, true>(st, st->tpr, x, y, direct); else launch_vector<T, false>(st, st->tpr, x, y, direct);
+        if (st->load_mode == 1) launch_vector<T, 1>(st, st->tpr, x, y, direct);
+        else if (st->load_mode == 2) launch_vector<T, 2>(st, st->tpr, x, y, direct);
+        else launch_vector<T, 0>(st, st->tpr, x, y, direct);
         scattered = scattered || !banded;
         break;
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
         const int grid = blocks_for((long long)st->parts * 32);
 #define SB_RB(V, P) row_block_kernel<T, V, P><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y, direct)
-        if (st->vec_ok) { if (direct.n > 0) SB_RB(true, true); else SB_RB(true, false); }
-        else { if (direct.n > 0) SB_RB(false, true); else SB_RB(false, false); }
+        if (st->rb_mode == 1) { if (direct.n > 0) SB_RB(1, true); else SB_RB(1, false); }
+        else if (st->rb_mode == 2) { if (direct.n > 0) SB_RB(2, true); else SB_RB(2, false); }
+        else { if (direct.n > 0) SB_RB(0, true); else SB_RB(0, false); }
 #undef SB_RB
         scattered = scattered || !banded;
         count_launch();
@@ -632,7 +727,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
             count_launch();
         }
         if (st->banner < m) {
-            csr_tail_kernel<T><<<blocks_for((long long)(m - st->banner) * 32), kThreads, 0, s>>>(st->banner, m, st->a_rowptr, st->a_col, val, x, y);
+            csr_tail_kernel<T><<<blocks_for((long long)(m - st->banner) * 32), kThreads, 0, s>>>(st->banner, m, st->long_thr, st->a_rowptr, st->a_col, val, x, y);
             count_launch();
         }
         break;
@@ -661,6 +756,14 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     default:
         set_error("handle has no kernel (%d)", st->kernel);
         return false;
+    }
+    if (st->lr_rows > 0) {  // hub rows / SELL overflow: segment sums, then one ordered add per row
+        long_seg_kernel<T><<<blocks_for((long long)st->lr_segs * 32), kThreads, 0, s>>>(
+            st->lr_segs, st->lr_seg_row, st->lr_row, st->lr_start, st->lr_seg_ptr, st->a_rowptr, st->a_col, val, x, (T *)st->lr_partial);
+        const int fgrid = blocks_for((long long)st->lr_rows * 32);
+        if (direct.n > 0) long_final_kernel<T, true><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
+        else long_final_kernel<T, false><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
+        count_launch(2);
     }
     if (banded) {
         if (peers.n > 0) band_reduce_kernel<T, true><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
@@ -899,6 +1002,9 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "csr5_bit_scansum_offset") return st->c5_bit_ss;
     if (k == "csr5_num_offsets") return st->c5_num_offsets;
     if (k == "csr5_tail_start") return st->c5_tail_start;
+    if (k == "long_rows") return st->lr_rows;
+    if (k == "long_segs") return st->lr_segs;
+    if (k == "long_thr") return st->long_thr;
     if (k == "device") return st->device;
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
@@ -906,7 +1012,8 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "far_permille") return (long long)(st->far_fraction * 1000.0);
     if (k == "active_rows") return st->a_m;
     if (k == "owns_csr") return st->owns_csr;
-    if (k == "vec_ok") return st->vec_ok;
+    if (k == "vec_ok") return st->load_mode == 1;
+    if (k == "load_mode") return st->load_mode;
     if (k == "dev_l2_bytes") return st->dev_l2;
     if (k == "dev_persist_max") return st->dev_persist_max;
     if (k == "dev_window_max") return st->dev_window_max;

@@ -51,6 +51,7 @@ def test_tile_rows_and_merge_coords(libpath, port, name):
 @pytest.mark.parametrize("name", list(BIG))
 def test_sell_permutation_is_reference_a13(libpath, port, name):
     a = BIG[name]()
+    api.set_option("sell_cap", 0)  # the reference's widths: every slice as wide as its longest row
     for sigma in (256, 64):
         api.set_option("sell_sigma", sigma)
         h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
@@ -74,6 +75,61 @@ def test_sell_permutation_is_reference_a13(libpath, port, name):
                     assert (blk[lens[r]:, lane] == -1).all()
         h.destroy()
     api.set_option("sell_sigma", 256)
+    api.set_option("sell_cap", 1024)
+
+
+def _capped_widths(rowptr, perm, cap=1024):
+    """numpy restatement of sell_width_kernel's rule (sell.cuh): slices that would be mostly padding take the
+    row length that minimises 32*l + 2*overflow + 64*rows_over; ties -> the larger width; never wider than cap."""
+    L = np.diff(rowptr)[perm].reshape(-1, 32).astype(np.int64)
+    w = L.max(axis=1)
+    for s in np.nonzero(32 * w > 2 * L.sum(axis=1))[0]:
+        l = L[s]
+        cost = np.array([32 * li + 2 * (l[l > li] - li).sum() + 64 * (l > li).sum() for li in l])
+        w[s] = l[cost == cost.min()].max()
+    return np.minimum(w, cap).astype(np.int32)
+
+
+@pytest.mark.parametrize("name", ["skew", "rmat12", "hub"])
+def test_sell_capped_slices_and_overflow(libpath, port, name):
+    """Default SELL on skewed matrices: same permutation as the reference, slice widths by the documented
+    cost rule, every row's first min(len, width) entries in its slice and the rest on the long-row list."""
+    a = (BIG[name] if name in BIG else all_cases()[name])()
+    api.set_option("sell_sigma", 64)
+    h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+    perm = h.structure("sell_perm", np.int32)
+    assert np.array_equal(perm, port.sell_perm(a.rowptr, 64))
+    w = h.structure("sell_width", np.int32)
+    assert np.array_equal(w, _capped_widths(a.rowptr, perm))
+    w_ref, f_ref = port.sell_chunks(a.rowptr, perm, 32)
+    assert (w <= w_ref).all() and (w < w_ref).any() and np.array_equal(h.structure("sell_full", np.int32), np.minimum(f_ref, w))
+    lens = np.diff(a.rowptr)
+    over = np.maximum(lens[perm] - np.repeat(w, 32), 0)
+    tail = lens[len(perm):]
+    n_long = int((over > 0).sum() + (tail > 4096).sum())
+    n_segs = int(((over + 2047) // 2048).sum() + ((tail[tail > 4096] + 2047) // 2048).sum())
+    assert (h.info("long_rows"), h.info("long_segs")) == (n_long, n_segs)
+    sp = h.structure("sell_slice_ptr", np.int64)
+    scol = h.structure("sell_col", np.int32)
+    for s in range(0, len(w), max(1, len(w) // 9)):
+        blk = scol[sp[s]:sp[s + 1]].reshape(-1, 32)
+        for lane in (0, 17, 31):
+            r = perm[s * 32 + lane]
+            k = min(lens[r], w[s])
+            assert np.array_equal(blk[:k, lane], a.col[a.rowptr[r]:a.rowptr[r] + k]) and (blk[k:, lane] == -1).all()
+    h.destroy()
+    api.set_option("sell_sigma", 256)
+
+
+def test_parallel_hub_rows_go_to_the_long_row_path(libpath):
+    a = all_cases()["hub"]()
+    h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
+    lens = np.diff(a.rowptr)
+    thr = h.info("long_thr")
+    assert thr == 512  # 256 * tpr, clamped to [512, 4096]
+    assert h.info("long_rows") == int((lens > thr).sum()) == 2
+    assert h.info("long_segs") == int(((lens[lens > thr] + 2047) // 2048).sum())
+    h.destroy()
 
 
 def test_sell_permutation_against_live_reference(libpath, ref):
