@@ -49,6 +49,15 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
  *   "force_merge"     1 = Method_Balanced2 always runs the merge-path kernel (default: only when a row is
  *                     long enough to starve a row block, the reference's own Balanced2 -> Balanced rule)
+ *   "vec"             how the CSR kernels read ColIdx / Val: -1 = automatic from the locality probe (default),
+ *                     1 = aligned 128/256-bit chunks, 2 = scalar loads through L1, 0 = scalar loads bypassing L1
+ *   "sell_cap"        widest SELL slice in columns (default 1024); slices that would be mostly padding are
+ *                     narrowed by a cost rule and the cut-off row tails go to the long-row path.  0 = the
+ *                     reference's widths (every slice as wide as its longest row)
+ *   "long_thr"        Method_Parallel leaves rows longer than this to the long-row path (0 = automatic:
+ *                     256 x lanes-per-row clamped to [512, 4096]; < 0 = never)
+ *   "pipeline"        1 (default) = spmv() with HOST x and y on a Method_Parallel handle overlaps the PCIe
+ *                     copies with the kernels (x in pieces, y in row chunks); 0 = copy, run, copy
  * Returns 0, or -1 for an unknown key. */
 SPMV_B200_API int spmv_b200_set_option(const char *key, long long value);
 SPMV_B200_API long long spmv_b200_get_option(const char *key);
@@ -78,6 +87,15 @@ enum {
 };
 SPMV_B200_API long long spmv_b200_info(spmv_Handle_t handle, const char *key);
 SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes);
+
+/* ---- method recommendation ("Matrix inspect and choose best method to run": an empty heading in the
+ * reference's README.md:222) ---------------------------------------------------------------------------
+ * Looks at the row-length distribution of a CSR (HOST RowPtr; pure host code, usable without a GPU) and
+ * returns the SPMV_METHODS value whose GPU layout measured fastest on matrices of that shape: Method_CSR5SPMV
+ * when more than a quarter of the non-zeros sit in rows much longer than the mean (power-law graphs),
+ * Method_Parallel for small matrices (fewer than 8192 rows: nothing to amortise a layout build), otherwise
+ * Method_SellCSigma.  Returns -1 on invalid arguments. */
+SPMV_B200_API int spmv_b200_recommend_method(int m, const int *RowPtr);
 
 /* kernels launched by this process on the spmv() path since load (for benchmark accounting) */
 SPMV_B200_API unsigned long long spmv_b200_launch_count(void);

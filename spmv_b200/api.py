@@ -36,7 +36,8 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_structure", "spmv_b200_launch_count", "spmv_b200_partition_rows", "spmv_b200_malloc",
     "spmv_b200_free", "spmv_b200_memcpy", "spmv_b200_gen_laplacian2d", "spmv_b200_gen_stencil27",
     "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free",
-    "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close"]
+    "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close",
+    "spmv_b200_recommend_method"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -94,6 +95,7 @@ def lib() -> C.CDLL:
     L.spmv_b200_structure.restype = ll
     L.spmv_b200_launch_count.restype = C.c_ulonglong
     L.spmv_b200_partition_rows.argtypes = [vp, i, i, vp]
+    L.spmv_b200_recommend_method.argtypes = [i, vp]
     L.spmv_b200_malloc.argtypes = [C.c_size_t]
     L.spmv_b200_malloc.restype = vp
     L.spmv_b200_free.argtypes = [vp]
@@ -283,6 +285,15 @@ def partition_rows(rowptr: np.ndarray, parts: int) -> np.ndarray:
     if lib().spmv_b200_partition_rows(rp.ctypes.data, len(rp) - 1, parts, out.ctypes.data) != 0:
         raise ValueError("bad partition arguments")
     return out
+
+
+def recommend_method(rowptr: np.ndarray) -> int:
+    """SPMV_METHODS value this library runs fastest for a matrix with these row lengths (host code)."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    r = lib().spmv_b200_recommend_method(len(rp) - 1, rp.ctypes.data)
+    if r < 0:
+        raise ValueError("bad arguments")
+    return r
 
 
 # ---------------------------------------------------------------------------------------------

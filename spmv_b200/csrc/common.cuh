@@ -25,6 +25,8 @@ void count_launch(int n = 1);
 constexpr int kThreads = 256;       // CTA size of every spmv-path kernel
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPipeChunks = 8;      // row chunks / x pieces of the pipelined host-pointer path
+constexpr int kMaxPieces = 64;      // >= kMaxBands (csr_kernels.cuh)
 constexpr int kMaxPeers = 8;        // extra y destinations of the fused SpMV + all-gather
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -56,8 +58,13 @@ struct DeviceState {
     void *val = nullptr;
     bool owns_csr = false;
 
-    // staging for host-side x / y
+    // staging for host-side x / y; the pipelined host path (CSR-vector kernel) copies x in pieces on s_in,
+    // computes row chunks as soon as their prefix of x has arrived, and returns finished chunks of y on s_out
     void *x_stage = nullptr, *y_stage = nullptr;
+    bool pipeline = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kMaxPieces] = {}, ev_out[kPipeChunks] = {}, ev_start = nullptr;
+    int chunk_xmax[kPipeChunks] = {};
 
     // Method_Parallel
     int tpr = 0;

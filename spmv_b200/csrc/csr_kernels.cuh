@@ -163,12 +163,13 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
 // ------------------------------------------------------------------------------------------------
 template <typename T, int TPR, int VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
-csr_vector_kernel(int m, int nnz, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
+csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
                   const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
 {
+    // rows [row0, m): the whole matrix in one launch, or one band / row chunk of the pipelined host path
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const long long row_l = gt / TPR;
+    const long long row_l = row0 + gt / TPR;
     const int sl = threadIdx.x & (TPR - 1);
     bool valid = row_l < m;
     const int row = valid ? (int)row_l : 0;
@@ -322,14 +323,36 @@ __global__ void band_scatter_kernel(int m, int bands, int band_cols, const int *
 }
 
 template <typename T, bool PEERS>
-__global__ void band_reduce_kernel(int m, int bands, const T *__restrict__ yv, T *__restrict__ y,
+__global__ void band_reduce_kernel(int row0, int row1, int m, int bands, const T *__restrict__ yv, T *__restrict__ y,
                                    const PeerList<T> peers)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
+    const int r = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= row1) return;
     T s = ldg_stream(yv + r);
     for (int b = 1; b < bands; ++b) s += ldg_stream(yv + (size_t)b * m + r);
     store_y<PEERS>(y, peers, r, s);
+}
+
+// Largest column index used by each of `chunks` equal row chunks (+1): the prefix of x a chunk needs.  Lets the
+// host-pointer path start a chunk as soon as that prefix has arrived over PCIe.
+__global__ void chunk_xmax_kernel(int m, int chunks, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                  int *__restrict__ xmax)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int mx = 0;
+    int c = 0;
+    if (r < m) {
+        c = (int)((long long)r * chunks / m);
+        for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) mx = max(mx, col[j] + 1);
+    }
+    // rows of one warp almost always share a chunk: reduce first, one integer atomic per warp (builder only)
+    const int c0 = __shfl_sync(kFull, c, 0);
+    if (__all_sync(kFull, c == c0 || r >= m)) {
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(xmax + c0, mx);
+    } else if (r < m && mx > 0) {
+        atomicMax(xmax + c, mx);
+    }
 }
 
 // y -> peers for the kernel families whose epilogue is not fused (stream-ordered after them)

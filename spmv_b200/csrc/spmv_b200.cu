@@ -49,7 +49,7 @@ struct Options {
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
-                                       {"long_thr", 0}};
+                                       {"long_thr", 0},    {"pipeline", 1}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -164,6 +164,11 @@ static void free_state(DeviceState *st)
     if (!st) return;
     DeviceGuard g(st->device);
     free_layouts(st);
+    for (int i = 0; i < kMaxPieces; ++i) if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
+    for (int i = 0; i < kPipeChunks; ++i) if (st->ev_out[i]) cudaEventDestroy(st->ev_out[i]);
+    if (st->ev_start) cudaEventDestroy(st->ev_start);
+    if (st->s_in) cudaStreamDestroy(st->s_in);
+    if (st->s_out) cudaStreamDestroy(st->s_out);
     if (st->owns_csr) { dfree(st->rowptr); dfree(st->col); dfree(st->val); }
     st->magic = 0;
     delete st;
@@ -351,6 +356,25 @@ static bool build_long_rows_threshold(DeviceState *st, int tpr)
     return build_long_rows(st, covered, /*accumulate=*/false);
 }
 
+// Host-pointer pipeline of the CSR-vector kernel (option "pipeline", default on): which prefix of x each of
+// the kPipeChunks row chunks needs (unbanded view; a band needs exactly its own slice of x).
+static bool build_pipeline(DeviceState *st)
+{
+    st->pipeline = false;
+    if (opt("pipeline") == 0 || st->lr_rows > 0 || st->m < (1 << 16)) return true;
+    if (st->x_bands > 1) { st->pipeline = st->x_bands <= kMaxPieces; return true; }
+    int *d = nullptr;
+    if (!dmalloc(&d, kPipeChunks)) return false;
+    SB_TRY(cudaMemsetAsync(d, 0, kPipeChunks * sizeof(int), st->stream));
+    chunk_xmax_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(st->m, kPipeChunks, st->rowptr, st->col, d);
+    const bool ok = SB_CUDA(cudaGetLastError()) &&
+                    SB_CUDA(cudaMemcpyAsync(st->chunk_xmax, d, kPipeChunks * sizeof(int), cudaMemcpyDeviceToHost, st->stream)) &&
+                    SB_CUDA(cudaStreamSynchronize(st->stream));
+    dfree(d);
+    st->pipeline = ok;
+    return ok;
+}
+
 static bool build_tiles(DeviceState *st, bool merge)
 {
     int ipt = (int)opt("tile_items");
@@ -496,7 +520,8 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
     case Method_Parallel:
         st->tpr = pick_tpr(st->nnz, st->a_m);
         st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
-        return build_long_rows_threshold(st, st->tpr);
+        if (!build_long_rows_threshold(st, st->tpr)) return false;
+        return build_pipeline(st);
     case Method_Balanced:
     case Method_Balanced2: {
         // mirror of the reference's demotion / promotion rule with the CALLER's nthreads (a10,
@@ -617,17 +642,25 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
 // launch dispatch (a3: the reference's spmv_functions[] table, common.c:85-94)
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC>
-static void launch_vector(DeviceState *st, int tpr, const T *x, T *y, const PeerList<T> &peers)
+static void launch_vector(DeviceState *st, int tpr, int row0, int row1, const T *x, T *y, const PeerList<T> &peers)
 {
-    const int m = st->a_m;
-    const int grid = blocks_for((long long)m * tpr);
+    const int grid = blocks_for((long long)(row1 - row0) * tpr);
+    if (grid <= 0) return;
 #define SB_CASE(N) case N: \
-        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
-        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(m, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(row0, row1, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
+        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(row0, row1, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers); \
         break;
     switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
 #undef SB_CASE
     count_launch();
+}
+
+template <typename T>
+static void launch_vector_mode(DeviceState *st, int row0, int row1, const T *x, T *y, const PeerList<T> &peers)
+{
+    if (st->load_mode == 1) launch_vector<T, 1>(st, st->tpr, row0, row1, x, y, peers);
+    else if (st->load_mode == 2) launch_vector<T, 2>(st, st->tpr, row0, row1, x, y, peers);
+    else launch_vector<T, 0>(st, st->tpr, row0, row1, x, y, peers);
 }
 
 // CSR-vector over rows [row0, m) only (the CSR tail of SELL)
@@ -680,9 +713,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         break;
     }
     case SPMV_B200_KERNEL_CSR_VECTOR:
-        if (st->load_mode == 1) launch_vector<T, 1>(st, st->tpr, x, y, direct);
-        else if (st->load_mode == 2) launch_vector<T, 2>(st, st->tpr, x, y, direct);
-        else launch_vector<T, 0>(st, st->tpr, x, y, direct);
+        launch_vector_mode<T>(st, 0, m, x, y, direct);
         scattered = scattered || !banded;
         break;
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
@@ -766,8 +797,8 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         count_launch(2);
     }
     if (banded) {
-        if (peers.n > 0) band_reduce_kernel<T, true><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
-        else band_reduce_kernel<T, false><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
+        if (peers.n > 0) band_reduce_kernel<T, true><<<blocks_for(st->m), kThreads, 0, s>>>(0, st->m, st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
+        else band_reduce_kernel<T, false><<<blocks_for(st->m), kThreads, 0, s>>>(0, st->m, st->m, st->x_bands, (const T *)st->v_y, y_out, peers);
         scattered = true;
         count_launch();
     }
@@ -776,6 +807,87 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         count_launch();
     }
     return SB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host x and host y through the CSR-vector kernel, pipelined over PCIe: x goes up in pieces on s_in, the
+// compute stream starts every band / row chunk as soon as the part of x it gathers from has arrived, and
+// finished chunks of y go back on s_out while later chunks are still being computed.  Same kernels, same
+// per-row arithmetic as the one-shot path: the bits of y do not depend on which path ran.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static bool run_pipelined(DeviceState *st, const T *hx, T *hy)
+{
+    if (!st->s_in) {
+        SB_TRY(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
+        SB_TRY(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxPieces; ++i) SB_TRY(cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming));
+        for (int i = 0; i < kPipeChunks; ++i) SB_TRY(cudaEventCreateWithFlags(&st->ev_out[i], cudaEventDisableTiming));
+        SB_TRY(cudaEventCreateWithFlags(&st->ev_start, cudaEventDisableTiming));
+    }
+    cudaStream_t s = st->stream;
+    T *xd = (T *)st->x_stage, *yd = (T *)st->y_stage;
+    const int m = st->m, n = st->n;
+    const bool banded = st->x_bands > 1;
+    const int pieces = banded ? st->x_bands : kPipeChunks;
+    PeerList<T> none;
+    none.n = 0;
+    for (int i = 0; i < kMaxPeers; ++i) none.p[i] = nullptr;
+    // whatever the caller queued on the compute stream before this call stays ahead of the copies
+    SB_TRY(cudaEventRecord(st->ev_start, s));
+    SB_TRY(cudaStreamWaitEvent(st->s_in, st->ev_start, 0));
+    SB_TRY(cudaStreamWaitEvent(st->s_out, st->ev_start, 0));
+    auto piece_lo = [&](int p) -> long long { return banded ? (long long)p * st->band_cols : (long long)n * p / pieces; };
+    auto piece_hi = [&](int p) -> long long {
+        long long hi = banded ? (long long)(p + 1) * st->band_cols : (long long)n * (p + 1) / pieces;
+        return (p == pieces - 1 || hi > n) ? n : hi;
+    };
+    for (int p = 0; p < pieces; ++p) {
+        const long long lo = piece_lo(p), hi = piece_hi(p);
+        if (hi > lo) SB_TRY(cudaMemcpyAsync(xd + lo, hx + lo, (size_t)(hi - lo) * sizeof(T), cudaMemcpyHostToDevice, st->s_in));
+        SB_TRY(cudaEventRecord(st->ev_in[p], st->s_in));
+    }
+    int waited = -1;
+    auto need_piece = [&](int p) -> bool {
+        for (; waited < p; ++waited) SB_TRY(cudaStreamWaitEvent(s, st->ev_in[waited + 1], 0));
+        return true;
+    };
+    auto chunk_out = [&](int c, int r0, int r1) -> bool {
+        SB_TRY(cudaEventRecord(st->ev_out[c], s));
+        SB_TRY(cudaStreamWaitEvent(st->s_out, st->ev_out[c], 0));
+        if (r1 > r0) SB_TRY(cudaMemcpyAsync(hy + r0, yd + r0, (size_t)(r1 - r0) * sizeof(T), cudaMemcpyDeviceToHost, st->s_out));
+        return true;
+    };
+    if (banded) {
+        const int K = st->x_bands;
+        for (int b = 0; b + 1 < K; ++b) {
+            if (!need_piece(b)) return false;
+            launch_vector_mode<T>(st, b * m, (b + 1) * m, xd, (T *)st->v_y, none);
+        }
+        if (!need_piece(K - 1)) return false;
+        for (int c = 0; c < kPipeChunks; ++c) {
+            const int r0 = (int)((long long)m * c / kPipeChunks), r1 = (int)((long long)m * (c + 1) / kPipeChunks);
+            launch_vector_mode<T>(st, (K - 1) * m + r0, (K - 1) * m + r1, xd, (T *)st->v_y, none);
+            if (r1 > r0) {
+                band_reduce_kernel<T, false><<<blocks_for(r1 - r0), kThreads, 0, s>>>(r0, r1, m, K, (const T *)st->v_y, yd, none);
+                count_launch();
+            }
+            if (!chunk_out(c, r0, r1)) return false;
+        }
+    } else {
+        for (int c = 0; c < kPipeChunks; ++c) {
+            const int r0 = (int)((long long)m * c / kPipeChunks), r1 = (int)((long long)m * (c + 1) / kPipeChunks);
+            int p = 0;
+            while (p < pieces - 1 && piece_hi(p) < st->chunk_xmax[c]) ++p;
+            if (!need_piece(p)) return false;
+            launch_vector_mode<T>(st, r0, r1, xd, yd, none);
+            if (!chunk_out(c, r0, r1)) return false;
+        }
+    }
+    SB_TRY(cudaGetLastError());
+    SB_TRY(cudaStreamSynchronize(st->s_out));  // every chunk of y is home (and so every kernel has run)
+    SB_TRY(cudaStreamSynchronize(st->s_in));   // x may be modified by the caller from here on
+    return true;
 }
 
 static DeviceState *state_of(const spmv_Handle *h)
@@ -862,15 +974,18 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
     const void *xd = Vector_Val_X;
     void *yd = Vector_Val_Y;
     const size_t xb = (size_t)st->n * st->vsize, yb = (size_t)st->m * st->vsize;
+    if (!x_dev && !st->x_stage && !SB_CUDA(cudaMalloc(&st->x_stage, xb ? xb : 1))) return;
+    if (!y_dev && !st->y_stage && !SB_CUDA(cudaMalloc(&st->y_stage, yb ? yb : 1))) return;
+    if (!x_dev && !y_dev && st->pipeline && st->n_peers == 0 && st->kernel == SPMV_B200_KERNEL_CSR_VECTOR && xb && yb) {
+        if (st->vsize == 8) run_pipelined<double>(st, (const double *)Vector_Val_X, (double *)Vector_Val_Y);
+        else run_pipelined<float>(st, (const float *)Vector_Val_X, (float *)Vector_Val_Y);
+        return;
+    }
     if (!x_dev) {
-        if (!st->x_stage && !SB_CUDA(cudaMalloc(&st->x_stage, xb ? xb : 1))) return;
         if (xb && !SB_CUDA(cudaMemcpyAsync(st->x_stage, Vector_Val_X, xb, cudaMemcpyHostToDevice, st->stream))) return;
         xd = st->x_stage;
     }
-    if (!y_dev) {
-        if (!st->y_stage && !SB_CUDA(cudaMalloc(&st->y_stage, yb ? yb : 1))) return;
-        yd = st->y_stage;
-    }
+    if (!y_dev) yd = st->y_stage;
     if (st->x_window && xd != st->window_base && xb) {
         // optional: mark x as persisting for everything launched on this stream
         cudaStreamAttrValue attr;
@@ -1002,6 +1117,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "csr5_bit_scansum_offset") return st->c5_bit_ss;
     if (k == "csr5_num_offsets") return st->c5_num_offsets;
     if (k == "csr5_tail_start") return st->c5_tail_start;
+    if (k == "pipeline") return st->pipeline;
     if (k == "long_rows") return st->lr_rows;
     if (k == "long_segs") return st->lr_segs;
     if (k == "long_thr") return st->long_thr;
@@ -1068,6 +1184,22 @@ int spmv_b200_partition_rows(const int *RowPtr, int m, int parts, int *splitter_
         splitter_out[g] = right_boundary(RowPtr, (int)b, m + 1) - 1;
     }
     return 0;
+}
+
+int spmv_b200_recommend_method(int m, const int *RowPtr)
+{
+    if (!RowPtr || m < 0) return -1;
+    if (m < 8192) return Method_Parallel;
+    const long long nnz = (long long)RowPtr[m] - RowPtr[0];
+    if (nnz <= 0) return Method_Parallel;
+    const double mean = (double)nnz / m;
+    const long long cut = (long long)(4.0 * mean) + 16;
+    long long heavy = 0;  // non-zeros in rows much longer than the mean
+    for (int r = 0; r < m; ++r) {
+        const long long len = (long long)RowPtr[r + 1] - RowPtr[r];
+        if (len > cut) heavy += len;
+    }
+    return (4 * heavy > nnz) ? Method_CSR5SPMV : Method_SellCSigma;
 }
 
 void *spmv_b200_malloc(size_t bytes)

@@ -92,6 +92,18 @@ def test_partition_rows_is_the_reference_splitter(libpath, golden, port, name):
         assert np.array_equal(s, port.splitter(A.rowptr, T))
 
 
+def test_recommend_method_by_row_length_distribution(libpath):
+    """regular matrices -> SELL, power-law -> CSR5, small -> Parallel (host code)."""
+    from spmv_b200 import matrices as M
+    assert api.recommend_method(M.laplacian2d(128).rowptr) == api.Method_SellCSigma
+    assert api.recommend_method(M.uniform_random(20000, 20000, 32, seed=1).rowptr) == api.Method_SellCSigma
+    assert api.recommend_method(M.stencil27(24).rowptr) == api.Method_SellCSigma
+    assert api.recommend_method(M.rmat(15, 16, dtype=np.float32).rowptr) == api.Method_CSR5SPMV
+    assert api.recommend_method(M.skewed(20000, 20000, max_len=9000).rowptr) == api.Method_CSR5SPMV
+    assert api.recommend_method(M.laplacian2d(48).rowptr) == api.Method_Parallel
+    assert api.recommend_method(np.zeros(9000, dtype=np.int32)) == api.Method_Parallel  # no non-zeros
+
+
 def test_no_device_is_a_loud_error_not_a_fallback(libpath):
     """Without a GPU, create must fail with a message and spmv must leave y untouched."""
     import torch

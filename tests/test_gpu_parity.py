@@ -242,3 +242,60 @@ def test_fused_peer_scatter_single_gpu_emulation(libpath, port, serial_ref):
             h.sync()
             assert torch.isnan(big).all() and bits_equal(y2.cpu().numpy(), yh)
             h.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+@pytest.mark.parametrize("case", ["lap_local", "uni_random", "uni_banded3", "tall", "wide_empty_tail"])
+def test_pipelined_host_path_same_bits_as_device_path(libpath, port, serial_ref, dt, case):
+    """Host x + host y on a Method_Parallel handle with >= 2^16 rows takes the PCIe-pipelined path (x in
+    pieces, row chunks start when their prefix of x has arrived, y chunks return early): it must give exactly
+    the bits of the one-shot device-pointer path, pinned or pageable memory, banded or not."""
+    import torch
+    bands = 0
+    if case == "lap_local":
+        a = M.laplacian2d(300, 260)                                   # chunk c needs only a prefix of x
+    elif case == "uni_random":
+        a = M.uniform_random(70000, 50000, 9, seed=31)                # every chunk needs all of x
+    elif case == "uni_banded3":
+        a, bands = M.uniform_random(66000, 90001, 24, seed=32), 3     # band b needs slice b of x
+    elif case == "tall":
+        a = M.uniform_random(200003, 1000, 3, seed=33)
+    else:
+        a = M.from_row_lengths([5] * 70000 + [0] * 3000, 300000)      # trailing empty rows, n >> m
+    a = a.astype(dt)
+    x = M.make_x(a.n, 77, dt)
+    api.set_option("x_bands", bands)
+    try:
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
+    finally:
+        api.set_option("x_bands", 0)
+    assert h.info("pipeline") == 1 and h.info("x_bands") == max(bands, 1)
+    dev = torch.device("cuda:0")
+    xd = torch.from_numpy(x).to(dev)
+    yd = torch.full((a.m,), float("nan"), dtype=xd.dtype, device=dev)
+    h.spmv(xd, yd)
+    h.sync()
+    y_dev = yd.cpu().numpy()
+    check_y(port, serial_ref, a, x, y_dev, api.Method_Parallel, "pipeline/" + case)
+    y_pageable = np.full(a.m, np.nan, dtype=dt)
+    h.spmv(x, y_pageable)
+    assert bits_equal(y_pageable, y_dev), case
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.full((a.m,), float("nan"), dtype=xd.dtype).pin_memory()
+    for _ in range(3):                                               # back to back: stage buffers are reused
+        yp.fill_(float("nan"))
+        h.spmv(xp, yp)
+        assert bits_equal(yp.numpy(), y_dev), case
+    api.set_option("pipeline", 0)
+    api.set_option("x_bands", bands)
+    try:
+        h2 = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
+    finally:
+        api.set_option("pipeline", 1)
+        api.set_option("x_bands", 0)
+    assert h2.info("pipeline") == 0
+    y_plain = np.full(a.m, np.nan, dtype=dt)
+    h2.spmv(x, y_plain)
+    assert bits_equal(y_plain, y_dev), case
+    h.destroy()
+    h2.destroy()
