@@ -255,7 +255,10 @@ static bool build_band_major(DeviceState *st)
     }
     if (bands == 0) {
         bands = 1;
-        if (xbytes > 0.9 * usable) {
+        // x up to ~1.2x the reach still gathers at >= 85 % of the L2 rate (profiles/r01_gather_probe.txt) and
+        // banding costs 15-20 % (virtual row pointers, partial y): R-MAT s24 fp32 (x = 64 MiB) measured 7-15 %
+        // FASTER unbanded, uniform fp64 (x = 128 MiB) 1.9x faster banded
+        if (xbytes > 1.2 * usable) {
             long long k = (long long)ceil(xbytes / (0.75 * usable));
             // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save,
             // and banding only pays when the accesses are NOT already diagonal-local
