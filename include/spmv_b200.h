@@ -37,7 +37,7 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
 /* ---- options (process-global, read when a handle is created) --------------------------------------
  * Also settable through the environment as SPMV_B200_<KEY IN CAPITALS>.  Keys:
  *   "sell_sigma"      sorting window of Method_SellCSigma (multiple of 32, <= 4096; default 256)
- *   "csr5_sigma"      nnz per lane of a CSR5 tile (4..16; default 16)
+ *   "csr5_sigma"      nnz per lane of a CSR5 tile (4, 8 or 16; default 0 = 8 on diagonal-local matrices, else 16)
  *   "block_nnz"       nnz per row block of Method_Balanced (default 512)
  *   "tile_items"      items per thread of the merge-path / equal-nnz tiles (4..16; default 8)
  *   "tpr"             force threads-per-row of Method_Parallel (power of two <= 32; 0 = from mean)
@@ -49,8 +49,11 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
  *   "force_merge"     1 = Method_Balanced2 always runs the merge-path kernel (default: only when a row is
  *                     long enough to starve a row block, the reference's own Balanced2 -> Balanced rule)
- *   "vec"             how the CSR kernels read ColIdx / Val: -1 = automatic from the locality probe (default),
- *                     1 = aligned 128/256-bit chunks, 2 = scalar loads through L1, 0 = scalar loads bypassing L1
+ *   "vec"             how the CSR kernels read ColIdx / Val: -1 = automatic (default: 4), 4 = predicated batches of
+ *                     8 scalar loads per lane through L1, 1 = aligned 128/256-bit chunks, 2 = scalar loads through
+ *                     L1 in a plain loop, 0 = scalar loads bypassing L1
+ *   "sell_variant"    SELL kernel flavour: -1 = automatic (default: 2 on diagonal-local matrices, else 0),
+ *                     0 = 8 columns per step / 40 registers, 1 = 8 / 32, 2 = 4 / 32, 3 = 4 pipelined, 4 = 8 pipelined
  *   "sell_cap"        widest SELL slice in columns (default 1024); slices that would be mostly padding are
  *                     narrowed by a cost rule and the cut-off row tails go to the long-row path.  0 = the
  *                     reference's widths (every slice as wide as its longest row)

@@ -89,7 +89,7 @@ struct DeviceState {
     void *carry_val = nullptr;      // [tiles] partial sum that belongs to a row started earlier
     int *carry_row = nullptr;       // [tiles] that row, or -1
     // Method_SellCSigma
-    int sigma = 0, banner = 0, slices = 0;
+    int sigma = 0, banner = 0, slices = 0, sell_variant = 0;
     long long padded = 0;
     int *sell_perm = nullptr, *sell_width = nullptr, *sell_full = nullptr, *sell_col = nullptr;
     long long *sell_slice_ptr = nullptr;

@@ -102,6 +102,7 @@ __device__ __forceinline__ void chunk_fma(int j, int start, int end, int nnz4, c
 // MODE 1: aligned 4-element chunks (128/256-bit loads).  MODE 0: scalar loads that bypass L1.  MODE 2: scalar
 // loads that allocate in L1 (L2 evict-first): the tpr lanes of a row walk it with stride tpr, so one 32-byte
 // sector serves several consecutive iterations of the same warp and should be fetched from L2 only once.
+// MODE 4 (the default): as MODE 2, in predicated batches of 8 entries per lane.
 template <typename T, int MODE>
 __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, int nnz4,
                                          const int *__restrict__ col, const T *__restrict__ val,
@@ -128,6 +129,32 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
                 sum += acc;
             }
         }
+    } else if (MODE == 4) {
+        // predicated batches of 8 entries per lane: every stream load of a batch is in flight before the first
+        // gather, so a row of up to 8*tpr entries costs three dependent memory round trips (rowptr, col/val, x)
+        // however it is aligned -- what a latency-bound (small, L2-cold) matrix needs
+        constexpr int B = 8;
+        int batches = 0;
+        T acc = 0;
+        for (int j = start + sl; j < end; j += B * tpr) {
+            int c[B];
+            T v[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const int jj = j + k * tpr;
+                c[k] = jj < end ? ldg_cached(col + jj, pf) : -1;
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                const int jj = j + k * tpr;
+                v[k] = jj < end ? ldg_cached(val + jj, pf) : (T)0;
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                if (c[k] >= 0) acc = fma_t(v[k], ldg_x(x + c[k], pl), acc);
+            if (++batches == kBlock / 2) { sum += acc; acc = 0; batches = 0; }
+        }
+        sum += acc;
     } else if (MODE == 2) {
         if (end - start <= 4 * kBlock * tpr) {
 #pragma unroll 4
@@ -189,6 +216,25 @@ csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict_
 // mean row length, so short-row and long-row regions of one matrix each get a fitting geometry.
 // Block 0 starts at row 0 (the reference leaves leading empty rows unwritten).
 // ------------------------------------------------------------------------------------------------
+template <typename T, int VEC, bool PEERS, int TPR>
+__device__ __forceinline__ void row_block_body(int r0, int r1, int lane, int nnz4, const int *__restrict__ rowptr,
+                                               const int *__restrict__ col, const T *__restrict__ val,
+                                               const T *__restrict__ x, T *__restrict__ y, const PeerList<T> &peers,
+                                               uint64_t pl, uint64_t pf)
+{
+    constexpr int rows_per_iter = 32 / TPR;
+    const int sub = lane / TPR, sl = lane & (TPR - 1);
+    for (int base = r0; base < r1; base += rows_per_iter) {
+        const int row = base + sub;
+        const bool valid = row < r1;
+        const int start = valid ? rowptr[row] : 0;
+        const int end = valid ? rowptr[row + 1] : 0;
+        T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz4, col, val, x, pl, pf);
+        sum = group_sum_c<T, TPR>(sum);
+        if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
+    }
+}
+
 template <typename T, int VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int *__restrict__ rowptr,
@@ -205,20 +251,17 @@ row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int
     if (nrows <= 0) return;
     const int nz = rowptr[r1] - rowptr[r0];
     const int avg = (nz + nrows - 1) / nrows;
-    int tpr = 1;
-    while (tpr < 32 && 4 * tpr < avg) tpr <<= 1;
-    const int rows_per_iter = 32 / tpr;
-    const int sub = lane / tpr, sl = lane & (tpr - 1);
     const int nnz4 = nnz & ~3;
-    for (int base = r0; base < r1; base += rows_per_iter) {
-        const int row = base + sub;
-        const bool valid = row < r1;
-        const int start = valid ? rowptr[row] : 0;
-        const int end = valid ? rowptr[row + 1] : 0;
-        T sum = row_partial<T, VEC>(start, end, sl, tpr, nnz4, col, val, x, pl, pf);
-        sum = group_sum(sum, tpr);
-        if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
-    }
+    // lanes per row from the block's own mean row length (warp-uniform): compile-time bodies so that the row
+    // walk unrolls and the butterfly has a fixed depth
+#define SB_BODY(N) row_block_body<T, VEC, PEERS, N>(r0, r1, lane, nnz4, rowptr, col, val, x, y, peers, pl, pf)
+    if (avg <= 4) SB_BODY(1);
+    else if (avg <= 8) SB_BODY(2);
+    else if (avg <= 16) SB_BODY(4);
+    else if (avg <= 32) SB_BODY(8);
+    else if (avg <= 64) SB_BODY(16);
+    else SB_BODY(32);
+#undef SB_BODY
 }
 
 // a9: csrSplitter of init_csrSplitter_balanced2 (reference parallel_balanced2_spmv.c:41-53).

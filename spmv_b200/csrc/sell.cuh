@@ -136,8 +136,10 @@ __global__ void sell_fill_kernel(int slices, const int *__restrict__ rowptr, con
     }
 }
 
-template <typename T, bool PEERS>
-__global__ void __launch_bounds__(kThreads)
+// U = columns per step (all 2U coalesced loads of a step are issued before its U gathers), MINB = CTAs per SM
+// the register allocation is held to, PIPE = issue the next step's stream loads before this step's gathers.
+template <typename T, bool PEERS, int U, int MINB, bool PIPE>
+__global__ void __launch_bounds__(kThreads, MINB)
 sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__restrict__ full,
             const int *__restrict__ perm, const int *__restrict__ scol, const T *__restrict__ sval,
             const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
@@ -149,26 +151,59 @@ sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__re
     const long long base = slice_ptr[s];
     const int w = (int)((slice_ptr[s + 1] - base) >> 5);
     const int f = full[s];
+    const int out_row = perm[(long long)s * kSellC + lane];
     const int *c = scol + base + lane;
     const T *v = sval + base + lane;
-    // blocked summation (8 columns -> 512 columns -> row) keeps the rounding error of a long row at
+    // blocked summation (U columns -> 512 columns -> row) keeps the rounding error of a long row at
     // ~sqrt(len/512) instead of ~sqrt(len) ulps; fixed order, so still bitwise reproducible
+    constexpr int kGroups = 512 / U;
     T sum = 0, mid = 0;
     int groups = 0;
     int j = 0;
     // columns every row of the slice owns: no padding test (the reference's `full` loop)
-    for (; j + 8 <= f; j += 8) {
-        int cc[8];
-        T vv[8];
+    if (PIPE) {
+        int cc[U];
+        T vv[U];
+        if (U <= f) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cc[k] = ldg_stream(c + (size_t)(j + k) * kSellC, pf);
+            for (int k = 0; k < U; ++k) cc[k] = ldg_stream(c + (size_t)k * kSellC, pf);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) vv[k] = ldg_stream(v + (size_t)(j + k) * kSellC, pf);
-        T part = 0;
+            for (int k = 0; k < U; ++k) vv[k] = ldg_stream(v + (size_t)k * kSellC, pf);
+        }
+        for (; j + U <= f; j += U) {
+            int nc[U];
+            T nv[U];
+            const bool more = j + 2 * U <= f;
+            if (more) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
-        mid += part;
-        if (++groups == 64) { sum += mid; mid = 0; groups = 0; }
+                for (int k = 0; k < U; ++k) nc[k] = ldg_stream(c + (size_t)(j + U + k) * kSellC, pf);
+#pragma unroll
+                for (int k = 0; k < U; ++k) nv[k] = ldg_stream(v + (size_t)(j + U + k) * kSellC, pf);
+            }
+            T part = 0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
+            mid += part;
+            if (++groups == kGroups) { sum += mid; mid = 0; groups = 0; }
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < U; ++k) { cc[k] = nc[k]; vv[k] = nv[k]; }
+            }
+        }
+    } else {
+        for (; j + U <= f; j += U) {
+            int cc[U];
+            T vv[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) cc[k] = ldg_stream(c + (size_t)(j + k) * kSellC, pf);
+#pragma unroll
+            for (int k = 0; k < U; ++k) vv[k] = ldg_stream(v + (size_t)(j + k) * kSellC, pf);
+            T part = 0;
+#pragma unroll
+            for (int k = 0; k < U; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
+            mid += part;
+            if (++groups == kGroups) { sum += mid; mid = 0; groups = 0; }
+        }
     }
     // remaining columns, padding (ColIdx == -1) masked as in the reference's `~idx ? ... : 0`
     for (; j < w; j += 4) {
@@ -185,10 +220,10 @@ sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__re
         for (int k = 0; k < 4; ++k)
             if (cc[k] >= 0) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
         mid += part;
-        if (++groups == 64) { sum += mid; mid = 0; groups = 0; }
+        if (++groups >= kGroups) { sum += mid; mid = 0; groups = 0; }
     }
     sum += mid;
-    store_y<PEERS>(y, peers, perm[(long long)s * kSellC + lane], sum);
+    store_y<PEERS>(y, peers, out_row, sum);
 }
 
 }  // namespace sb

@@ -45,11 +45,12 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 
 struct Options {
     std::mutex mu;
-    std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 16}, {"block_nnz", 512},
+    std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 0}, {"block_nnz", 512},
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
-                                       {"long_thr", 0},    {"pipeline", 1}};
+                                       {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
+                                       {"rb_auto", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -200,18 +201,20 @@ static void apply_device_limits(DeviceState *st)
     st->x_window = opt("x_window") != 0;
 }
 
-// How the CSR kernels read ColIdx / Val.  Option "vec": -1 = automatic from the locality probe, 1 = aligned
-// 4-element chunks (128/256-bit loads; needs 32-byte aligned arrays), 2 = scalar loads through L1, 0 = scalar
-// loads bypassing L1.
+// How the CSR kernels read ColIdx / Val.  Option "vec": -1 = automatic, 4 = predicated batches of 8 scalar
+// loads per lane through L1 (every stream load of a row in flight before its first gather), 1 = aligned
+// 4-element chunks (128/256-bit loads; needs 32-byte aligned arrays), 2 = scalar loads through L1 in a plain
+// loop, 0 = scalar loads bypassing L1.  Measured (fraction of the HBM peak, Method_Parallel, modes 1 / 2 / 4):
+// C1 0.50 / 0.60 / 0.62, C2 0.385 / 0.36 / 0.40, C3 - / 0.26 / 0.28, C4 0.69 / 0.74 / 0.89 -- mode 4 everywhere.
 static void resolve_load_mode(DeviceState *st)
 {
     long long mode = opt("vec");
-    const bool forced = mode >= 0 && mode <= 2;
-    if (!forced) mode = (st->far_fraction > 0.25) ? 1 : 2;
+    const bool forced = mode >= 0 && mode <= 4 && mode != 3;
+    if (!forced) mode = 4;
     if (mode == 1 && !st->aligned) mode = 2;
     st->load_mode = (int)mode;
-    // the row-block kernel (run-time lanes per row) measured faster with chunk loads on every matrix
-    st->rb_mode = forced ? (int)mode : (st->aligned ? 1 : 2);
+    // the row-block kernel (run-time lanes per row): aligned chunks unless told otherwise
+    st->rb_mode = (forced && mode < 3) ? (int)mode : ((st->aligned && opt("rb_auto") == 0) ? 1 : st->load_mode);
 }
 
 static int pick_tpr(long long nnz, int m)
@@ -416,6 +419,10 @@ static bool build_sell(DeviceState *st)
     st->slices = st->banner / kSellC;
     st->tpr = pick_tpr(st->nnz, st->a_m);  // for the CSR tail rows [banner, m)
     st->kernel = SPMV_B200_KERNEL_SELL;
+    // HBM-bound (diagonal-local) matrices want every warp slot filled: 4 columns per step in 32 registers
+    // (C4: 0.86 -> 0.98 of the measured peak); gather-bound ones run best with 8 columns per step (C2: 0.43 vs 0.39)
+    st->sell_variant = (int)opt("sell_variant");
+    if (st->sell_variant < 0 || st->sell_variant > 4) st->sell_variant = (st->far_fraction > 0.25) ? 0 : 2;
     // covered[r]: entries of row r stored in its slice (sell_width_kernel); tail rows [banner, m) stay CSR,
     // except hub rows, which csr_tail_kernel zeroes and the long-row path then adds as a whole
     long long cap_opt = opt("sell_cap");  // 0 = off (the reference's widths), else the widest slice allowed
@@ -459,8 +466,8 @@ static bool build_sell(DeviceState *st)
 template <typename T>
 static bool build_csr5(DeviceState *st)
 {
-    int sigma = (int)opt("csr5_sigma");
-    if (sigma != 4 && sigma != 8 && sigma != 16) sigma = 16;
+    int sigma = (int)opt("csr5_sigma");  // 0 = automatic: 8 on diagonal-local matrices (fewer registers, more warps in flight)
+    if (sigma != 4 && sigma != 8 && sigma != 16) sigma = (st->far_fraction >= 0.0 && st->far_fraction <= 0.25) ? 8 : 16;
     st->c5_sigma = sigma;
     // anonymouslib_avx2.h:124-146 at omega = 32
     int base = 2, by = 1;
@@ -662,6 +669,7 @@ template <typename T>
 static void launch_vector_mode(DeviceState *st, int row0, int row1, const T *x, T *y, const PeerList<T> &peers)
 {
     if (st->load_mode == 1) launch_vector<T, 1>(st, st->tpr, row0, row1, x, y, peers);
+    else if (st->load_mode == 4) launch_vector<T, 4>(st, st->tpr, row0, row1, x, y, peers);
     else if (st->load_mode == 2) launch_vector<T, 2>(st, st->tpr, row0, row1, x, y, peers);
     else launch_vector<T, 0>(st, st->tpr, row0, row1, x, y, peers);
 }
@@ -724,6 +732,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
 #define SB_RB(V, P) row_block_kernel<T, V, P><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y, direct)
         if (st->rb_mode == 1) { if (direct.n > 0) SB_RB(1, true); else SB_RB(1, false); }
         else if (st->rb_mode == 2) { if (direct.n > 0) SB_RB(2, true); else SB_RB(2, false); }
+        else if (st->rb_mode == 4) { if (direct.n > 0) SB_RB(4, true); else SB_RB(4, false); }
         else { if (direct.n > 0) SB_RB(0, true); else SB_RB(0, false); }
 #undef SB_RB
         scattered = scattered || !banded;
@@ -751,12 +760,16 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     case SPMV_B200_KERNEL_SELL: {
         if (st->slices > 0) {
             const PeerList<T> &sp = (st->banner == m) ? direct : none;
-            if (sp.n > 0)
-                sell_kernel<T, true><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
-                    st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp);
-            else
-                sell_kernel<T, false><<<blocks_for((long long)st->slices * 32), kThreads, 0, s>>>(
-                    st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp);
+            const int sgrid = blocks_for((long long)st->slices * 32);
+#define SB_SELL(P, U, MINB, PIPE) sell_kernel<T, P, U, MINB, PIPE><<<sgrid, kThreads, 0, s>>>( \
+                st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp)
+            if (sp.n > 0) SB_SELL(true, 8, 6, false);
+            else if (st->sell_variant == 1) SB_SELL(false, 8, 8, false);
+            else if (st->sell_variant == 2) SB_SELL(false, 4, 8, false);
+            else if (st->sell_variant == 3) SB_SELL(false, 4, 6, true);
+            else if (st->sell_variant == 4) SB_SELL(false, 8, 4, true);
+            else SB_SELL(false, 8, 6, false);
+#undef SB_SELL
             scattered = scattered || (!banded && st->banner == m);
             count_launch();
         }

@@ -161,7 +161,7 @@ def test_csr5_descriptors_are_reference_a16_a18(libpath, port, name):
             assert np.array_equal(h.structure("csr5_offsets", np.int32), want["offsets"])
             assert np.array_equal(h.structure("csr5_col", np.int32), want["col_t"])
         h.destroy()
-    api.set_option("csr5_sigma", 16)
+    api.set_option("csr5_sigma", 0)
 
 
 def test_generators_match_numpy_bit_for_bit(libpath):
