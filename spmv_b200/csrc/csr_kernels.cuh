@@ -191,9 +191,13 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
 template <typename T, int TPR, int VEC, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
-                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers)
+                  const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers,
+                  int fuse_bands, int band_m, const T *__restrict__ vy)
 {
-    // rows [row0, m): the whole matrix in one launch, or one band / row chunk of the pipelined host path
+    // rows [row0, m): the whole matrix in one launch, or one band / row chunk of the pipelined host path.
+    // fuse_bands > 0: these are rows of the LAST band of a band-major copy; the partial sums of the fuse_bands
+    // earlier bands (vy, complete: written by an earlier launch) are folded in here, in band order, and the
+    // final value goes to row (virtual row - fuse_bands*band_m) of y -- band_reduce_kernel without its own pass.
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long row_l = row0 + gt / TPR;
@@ -203,9 +207,18 @@ csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict_
     int start = valid ? rowptr[row] : 0;
     int end = valid ? rowptr[row + 1] : 0;
     if (end - start > long_thr) { valid = false; end = start; }  // hub row: left to the long-row path
+    int out_row = row;
+    T prev = 0;
+    if (fuse_bands > 0) {
+        out_row = row - fuse_bands * band_m;
+        if (valid && sl == 0) {  // issued before the row walk: in flight while the row is being summed
+            prev = ldg_stream(vy + out_row);
+            for (int b = 1; b < fuse_bands; ++b) prev += ldg_stream(vy + (size_t)b * band_m + out_row);
+        }
+    }
     T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
     sum = group_sum_c<T, TPR>(sum);
-    if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
+    if (valid && sl == 0) store_y<PEERS>(y, peers, out_row, fuse_bands > 0 ? prev + sum : sum);
 }
 
 // ------------------------------------------------------------------------------------------------
