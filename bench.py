@@ -476,7 +476,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--method", default="parallel", choices=list(METHODS))
-    ap.add_argument("--also", default="balanced2", help="comma list of further methods timed after the primary")
+    ap.add_argument("--also", default="balanced2,sell", help="comma list of further methods timed after the primary")
     ap.add_argument("--power-iters", type=int, default=50)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--small", action="store_true", help="64x smaller matrices (script debugging only; not a bench)")
