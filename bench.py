@@ -60,6 +60,12 @@ def make_workload(name: str, rank: int, world: int, small: bool):
         A = api.gen_uniform(rows, n, 16, M.SEED_C5, rank * rows, False, 8)
         desc = f"C5-family uniform-random {n}x{n}, 16 nnz/row, fp64 CSR ({rows} rows/GPU)"
         return A, n, 8, desc, M.SEED_C5
+    if name == "c5shard":
+        # exactly one GPU's share of C5 at 8 GPUs, on ONE GPU: 2^25 rows of the 2^28-column matrix (x = 2 GiB)
+        rows = 1 << (25 - sh)
+        n = rows * 8
+        A = api.gen_uniform(rows, n, 16, M.SEED_C5, rank * rows, False, 8)
+        return A, n, 8, f"C5 shard: rows [0, {rows}) of uniform-random {n}x{n}, 16 nnz/row, fp64 CSR", M.SEED_C5
     if world != 1:
         raise SystemExit(f"workload {name} is single-GPU")
     if name == "c1":
@@ -474,7 +480,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "c5shard"])
     ap.add_argument("--method", default="parallel", choices=list(METHODS))
     ap.add_argument("--also", default="balanced2,sell", help="comma list of further methods timed after the primary")
     ap.add_argument("--power-iters", type=int, default=50)

@@ -44,6 +44,9 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "x_bands"         column bands of the band-major layout that keeps the gathered slice of x inside L2
  *                     (0 = automatic from n and the L2 size, 1 = off, 2..64 forced); every method except
  *                     Method_Serial can run on the band-major copy
+ *   "coo_bands"       column bands stored as COO lists sorted by row, for matrices whose bands would hold fewer than
+ *                     4 non-zeros per row (0 = automatic, -1 = never, 2..64 forced); replaces the kernel of every
+ *                     method except Method_Serial
  *   "l2_persist"      bytes of L2 set aside for persisting lines at create (0 = leave, -1 = device max)
  *   "l2_fetch"        cudaLimitMaxL2FetchGranularity at create (0 = leave; 32 / 64 / 128)
  *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
@@ -86,7 +89,9 @@ enum {
     SPMV_B200_KERNEL_MERGE_PATH = 4,   /* Method_Balanced2 */
     SPMV_B200_KERNEL_NNZ_SPLIT = 5,    /* Method_Balanced_Yid */
     SPMV_B200_KERNEL_SELL = 6,         /* Method_SellCSigma */
-    SPMV_B200_KERNEL_CSR5 = 7          /* Method_CSR5SPMV */
+    SPMV_B200_KERNEL_CSR5 = 7,         /* Method_CSR5SPMV */
+    SPMV_B200_KERNEL_BAND_COO = 8      /* any method but Method_Serial when x needs so many column bands that
+                                          they are hyper-sparse (see "coo_bands") */
 };
 SPMV_B200_API long long spmv_b200_info(spmv_Handle_t handle, const char *key);
 SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes);

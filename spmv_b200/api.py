@@ -26,7 +26,7 @@ METHOD_NAMES = ["Method_Serial", "Method_Parallel", "Method_Balanced", "Method_B
                 "Method_BalancedYid", "Method_SellCSigma", "Method_Csr5Spmv"]
 
 KERNEL_NAMES = {0: "none", 1: "csr_reforder", 2: "csr_vector", 3: "row_blocks", 4: "merge_path",
-                5: "nnz_split", 6: "sell", 7: "csr5"}
+                5: "nnz_split", 6: "sell", 7: "csr5", 8: "band_coo"}
 
 # every symbol include/spmv.h and include/spmv_b200.h declare
 EXPORTED_FUNCTIONS = [

@@ -94,6 +94,11 @@ struct DeviceState {
     int *sell_perm = nullptr, *sell_width = nullptr, *sell_full = nullptr, *sell_col = nullptr;
     long long *sell_slice_ptr = nullptr;
     void *sell_val = nullptr;
+    // hyper-sparse column bands as COO lists (band_coo.cuh): x_bands = K but the active view stays the CSR
+    int coo_bands = 0, coo_tiles = 0;
+    int coo_ptr[kMaxPieces + 1] = {};  // entry range of every band (host copy)
+    int *coo_row = nullptr, *coo_col = nullptr;
+    void *coo_val = nullptr;
     // long rows / row tails left over by the main kernel of Method_Parallel and Method_SellCSigma (long_rows.cuh)
     int long_thr = 0x7fffffff;      // CSR-vector kernels skip rows longer than this
     int lr_rows = 0, lr_segs = 0;

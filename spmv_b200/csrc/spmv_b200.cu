@@ -9,6 +9,7 @@
 #include <map>
 #include <cmath>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
 #include "csr_kernels.cuh"
@@ -16,6 +17,7 @@
 #include "sell.cuh"
 #include "csr5.cuh"
 #include "long_rows.cuh"
+#include "band_coo.cuh"
 
 namespace sb {
 
@@ -50,7 +52,7 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"rb_auto", 0}};
+                                       {"rb_auto", 0},     {"coo_bands", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -151,6 +153,9 @@ static void free_layouts(DeviceState *st)
     dfree(st->c5_off); st->c5_off = nullptr;
     dfree(st->c5_col); st->c5_col = nullptr;
     dfree(st->c5_val); st->c5_val = nullptr;
+    dfree(st->coo_row); st->coo_row = nullptr;
+    dfree(st->coo_col); st->coo_col = nullptr;
+    dfree(st->coo_val); st->coo_val = nullptr;
     dfree(st->lr_row); st->lr_row = nullptr;
     dfree(st->lr_start); st->lr_start = nullptr;
     dfree(st->lr_seg_ptr); st->lr_seg_ptr = nullptr;
@@ -265,9 +270,13 @@ static bool build_band_major(DeviceState *st)
             long long k = (long long)ceil(xbytes / (0.75 * usable));
             // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save,
             // and banding only pays when the accesses are NOT already diagonal-local
-            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0 && st->far_fraction > 0.25) bands = k;
+            if (k <= kMaxBands && st->far_fraction > 0.25) {
+                if ((double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
+                else if (opt("coo_bands") == 0) st->coo_bands = (int)k;  // too sparse for virtual rows: COO bands
+            }
         }
     }
+    if (opt("coo_bands") >= 2) { st->coo_bands = (int)(opt("coo_bands") > kMaxBands ? kMaxBands : opt("coo_bands")); bands = 1; }
     if (bands <= 1) return true;
     if (bands > kMaxBands) bands = kMaxBands;
     if ((long long)st->m * bands > 0x7fffffffLL - 8192) return true;
@@ -520,9 +529,63 @@ static bool build_csr5(DeviceState *st)
     return true;
 }
 
+// COO column bands (band_coo.cuh): stable bucketing of the CSR entries by col / band_cols
+template <typename T>
+static bool build_band_coo(DeviceState *st)
+{
+    const int K = st->coo_bands, nnz = st->nnz, m = st->m;
+    st->x_bands = K;
+    st->band_cols = (int)(((long long)st->n + K - 1) / K);
+    int *ent_row = nullptr, *idx_in = nullptr, *idx_out = nullptr, *d_ptr = nullptr;
+    unsigned char *key_in = nullptr, *key_out = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    bool ok = dmalloc(&ent_row, (size_t)nnz) && dmalloc(&idx_in, (size_t)nnz) && dmalloc(&idx_out, (size_t)nnz) &&
+              dmalloc(&key_in, (size_t)nnz) && dmalloc(&key_out, (size_t)nnz) && dmalloc(&d_ptr, (size_t)K + 1) &&
+              dmalloc(&st->coo_row, (size_t)nnz + 8) && dmalloc(&st->coo_col, (size_t)nnz + 8) &&
+              SB_CUDA(cudaMalloc(&st->coo_val, ((size_t)nnz + 8) * sizeof(T)));
+    if (ok) {
+        coo_expand_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->band_cols, K, st->rowptr, st->col, ent_row, key_in);
+        coo_iota_kernel<<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_in);
+        int bits = 1;
+        while ((1 << bits) < K) ++bits;
+        ok = SB_CUDA(cudaGetLastError()) &&
+             SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, idx_in, idx_out, nnz, 0, bits, st->stream)) &&
+             SB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1)) &&
+             SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, idx_in, idx_out, nnz, 0, bits, st->stream));
+    }
+    if (ok) {
+        coo_gather_kernel<T><<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_out, ent_row, st->col, (const T *)st->val,
+                                                                          st->coo_row, st->coo_col, (T *)st->coo_val);
+        coo_band_ptr_kernel<<<1, kThreads, 0, st->stream>>>(nnz, K, key_out, d_ptr);
+        ok = SB_CUDA(cudaGetLastError()) &&
+             SB_CUDA(cudaMemcpyAsync(st->coo_ptr, d_ptr, ((size_t)K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st->stream)) &&
+             SB_CUDA(cudaStreamSynchronize(st->stream));
+    }
+    dfree(ent_row); dfree(idx_in); dfree(idx_out); dfree(key_in); dfree(key_out); dfree(d_ptr); dfree(tmp);
+    if (!ok) return false;
+    st->coo_tiles = 0;
+    for (int b = 0; b < K; ++b) st->coo_tiles += ceil_div((long long)st->coo_ptr[b + 1] - st->coo_ptr[b], kCooTile);
+    st->tiles = st->coo_tiles;
+    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)(st->coo_tiles ? st->coo_tiles : 1) * sizeof(T)))) return false;
+    if (!dmalloc(&st->carry_row, (size_t)st->coo_tiles)) return false;
+    st->kernel = SPMV_B200_KERNEL_BAND_COO;
+    return true;
+}
+
 template <typename T>
 static bool build_method(DeviceState *st, spmv_Handle *h, int method)
 {
+    if (st->coo_bands > 1 && method != Method_Serial) {
+        if (method == Method_Balanced || method == Method_Balanced2) {
+            // keep what a client reads from the handle: the reference's Balanced <-> Balanced2 rule (a10)
+            st->ref_T = (int)(h->nthreads ? (h->nthreads > (1u << 24) ? (1u << 24) : h->nthreads) : 1);
+            int ref_starved = 0;
+            if (!build_splitter(st, st->m, st->rowptr, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
+            h->spmvMethod = ref_starved ? Method_Balanced2 : Method_Balanced;
+        }
+        return build_band_coo<T>(st);
+    }
     switch (method) {
     case Method_Serial:
         st->kernel = SPMV_B200_KERNEL_CSR_REFORDER;
@@ -705,6 +768,32 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     if (st->kernel == SPMV_B200_KERNEL_NONE) {  // nnz == 0: y = 0
         fill_zero_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out);
         count_launch();
+        return SB_CUDA(cudaGetLastError());
+    }
+    if (st->kernel == SPMV_B200_KERNEL_BAND_COO) {
+        // y = 0, then one launch per band (ascending: each adds its segment sums to y), then the carries
+        if (!SB_CUDA(cudaMemsetAsync(y_out, 0, (size_t)st->m * sizeof(T), s))) return false;
+        int tile_base = 0;
+        for (int b = 0; b < st->coo_bands; ++b) {
+            const int e0 = st->coo_ptr[b], e1 = st->coo_ptr[b + 1];
+            const int tiles = ceil_div((long long)e1 - e0, kCooTile);
+            if (tiles <= 0) continue;
+            band_coo_kernel<T><<<tiles, kThreads, 0, s>>>(e0, e1, tile_base, st->coo_row, st->coo_col, (const T *)st->coo_val, x, y_out,
+                                                         (T *)st->carry_val, st->carry_row);
+            tile_base += tiles;
+            count_launch();
+        }
+        if (tile_base > 0) {
+            carry_fixup_kernel<T><<<blocks_for(tile_base), kThreads, 0, s>>>(tile_base, st->carry_row, (const T *)st->carry_val, y_out);
+            count_launch();
+        }
+        if (st->n_peers > 0) {
+            PeerList<T> pr;
+            pr.n = st->n_peers;
+            for (int i = 0; i < kMaxPeers; ++i) pr.p[i] = (T *)st->peers[i];
+            peer_copy_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out, pr);
+            count_launch();
+        }
         return SB_CUDA(cudaGetLastError());
     }
     // the active view: the CSR itself, or its band-major copy writing the virtual y
@@ -1142,6 +1231,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "device") return st->device;
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
+    if (k == "coo_bands") return st->coo_bands;
     if (k == "band_cols") return st->band_cols;
     if (k == "far_permille") return (long long)(st->far_fraction * 1000.0);
     if (k == "active_rows") return st->a_m;
@@ -1179,6 +1269,14 @@ long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst,
     else if (k == "csr5_offsets") { src = st->c5_off; bytes = (size_t)st->c5_num_offsets * 4; }
     else if (k == "csr5_col") { src = st->c5_col; bytes = (size_t)st->nnz * 4; }
     else if (k == "csr5_val") { src = st->c5_val; bytes = (size_t)st->nnz * st->vsize; }
+    else if (k == "coo_row") { src = st->coo_row; bytes = st->coo_row ? (size_t)st->nnz * 4 : 0; }
+    else if (k == "coo_col") { src = st->coo_col; bytes = st->coo_col ? (size_t)st->nnz * 4 : 0; }
+    else if (k == "coo_ptr") {
+        if (!dst) return st->coo_bands > 1 ? (long long)(st->coo_bands + 1) * 4 : 0;
+        if (st->coo_bands <= 1 || dst_bytes < (size_t)(st->coo_bands + 1) * 4) return -1;
+        memcpy(dst, st->coo_ptr, (size_t)(st->coo_bands + 1) * 4);
+        return (long long)(st->coo_bands + 1) * 4;
+    }
     else if (k == "band_rowptr") { src = st->v_rowptr; bytes = st->v_rowptr ? ((size_t)st->a_m + 1) * 4 : 0; }
     else if (k == "band_col") { src = st->v_col; bytes = st->v_col ? (size_t)st->nnz * 4 : 0; }
     else return -1;

@@ -299,3 +299,53 @@ def test_pipelined_host_path_same_bits_as_device_path(libpath, port, serial_ref,
     assert bits_equal(y_plain, y_dev), case
     h.destroy()
     h2.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+@pytest.mark.parametrize("bands", [2, 7])
+def test_coo_band_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
+    """Hyper-sparse column bands as row-sorted COO lists (band_coo.cuh), forced on small matrices: every
+    method but Method_Serial runs the band_coo kernel; same error bound, reproducible, and the layout is the
+    stable bucketing of the CSR entries by col // band_cols."""
+    for name in ("uni32", "uni5r", "skew", "hub", "lead_trail_empty", "lap48", "one_long_row", "one_row", "tiny_m3", "empties"):
+        a = CASES[name]().astype(dt)
+        x = M.make_x(a.n, 5, dt)
+        for method in METHODS:
+            api.set_option("coo_bands", bands)
+            try:
+                h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+            finally:
+                api.set_option("coo_bands", 0)
+            tag = f"coo{bands}/{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
+            if method == api.Method_Serial:
+                assert h.kernel == "csr_reforder" and h.info("coo_bands") == 0
+            else:
+                assert h.kernel == "band_coo" and h.info("coo_bands") == bands and h.info("x_bands") == bands, tag
+            y = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y)
+            assert not np.isnan(y).any(), tag
+            check_y(port, serial_ref, a, x, y, method, tag)
+            y2 = np.full(a.m, np.nan, dtype=dt)
+            h.spmv(x, y2)
+            assert bits_equal(y, y2), tag
+            if method == api.Method_Parallel:
+                bc = h.info("band_cols")
+                assert bc == -(-a.n // bands)
+                ptr = h.structure("coo_ptr", np.int32)
+                assert len(ptr) == bands + 1
+                rows = np.repeat(np.arange(a.m, dtype=np.int32), np.diff(a.rowptr))
+                band = np.minimum(a.col // bc, bands - 1)
+                order = np.argsort(band, kind="stable")
+                assert np.array_equal(ptr, np.searchsorted(band[order], np.arange(bands + 1)).astype(np.int32))
+                assert np.array_equal(h.structure("coo_row", np.int32), rows[order])
+                assert np.array_equal(h.structure("coo_col", np.int32), a.col[order])
+            h.destroy()
+    # a Balanced / Balanced2 handle still mirrors the reference's demotion rule for clients that read it
+    a = CASES["longrow0"]()
+    api.set_option("coo_bands", 2)
+    try:
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Balanced, nthreads=4)
+    finally:
+        api.set_option("coo_bands", 0)
+    assert h.kernel == "band_coo" and h.struct.spmvMethod == api.Method_Balanced2
+    h.destroy()
