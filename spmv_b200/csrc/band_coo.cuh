@@ -11,7 +11,8 @@
 //     segment at a thread's end travels to the following threads through a block-wide scan-by-key;
 //   * a segment that ends inside the tile is added to y by exactly one thread (plain read-modify-write: within a
 //     launch no other thread touches that row, earlier bands are earlier launches); the segment still open at
-//     the tile's end goes to carry_val[tile] and carry_fixup_kernel adds the carries in tile order at the end.
+//     the tile's end goes to carry_val[tile] and carry_fixup_kernel adds the band's carries in tile order right
+//     after the band's launch (per band: the same row may carry in several bands).
 // No atomics, fixed order: bitwise reproducible.  The reference has no counterpart (its x lives in one NUMA
 // domain's DRAM behind the CPU caches); this is the GPU answer to "x does not fit the last-level cache".
 #pragma once
@@ -123,6 +124,13 @@ band_coo_kernel(int e0, int e1, int tile_base, const int *__restrict__ brow, con
             }
         }
     }
+    // y += segment sums.  The rows a thread closes are distinct and nobody else touches them in this launch, so
+    // all reads of y are issued up front -- 8 independent loads that fly while the block-wide scan runs -- and
+    // the writes follow at the end.
+    T old[kCooIpt];
+#pragma unroll
+    for (int k = 0; k < kCooIpt; ++k) old[k] = out_row[k] >= 0 ? y[out_row[k]] : (T)0;
+
     int ex_key, agg_key;
     T ex_val, agg_val;
     block_scan_by_key<T>(open_key, run, ex_key, ex_val, agg_key, agg_val, s_k, s_v);
@@ -134,7 +142,7 @@ band_coo_kernel(int e0, int e1, int tile_base, const int *__restrict__ brow, con
             T v = out_val[k];
             if (first && ex_key == out_row[k]) v = ex_val + v;  // the part that sits in the preceding threads
             first = false;
-            y[out_row[k]] = y[out_row[k]] + v;                 // sole writer of this row in this launch
+            stg_y(y + out_row[k], old[k] + v);
         }
     }
     if (tid == 0) {

@@ -133,7 +133,7 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
         // predicated batches of 8 entries per lane: every stream load of a batch is in flight before the first
         // gather, so a row of up to 8*tpr entries costs three dependent memory round trips (rowptr, col/val, x)
         // however it is aligned -- what a latency-bound (small, L2-cold) matrix needs
-        constexpr int B = 8;
+        constexpr int B = 8;  // (4 per batch in 32 registers at full occupancy measured slower on every matrix)
         int batches = 0;
         T acc = 0;
         for (int j = start + sl; j < end; j += B * tpr) {
@@ -188,16 +188,17 @@ __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, in
 // the OpenMP row loop becomes a grid of sub-warps, TPR lanes per row with TPR = 2^k ~ mean row
 // length / 4 chosen at create.  Fixed butterfly reduction => bitwise reproducible.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int TPR, int VEC, bool PEERS>
+template <typename T, int TPR, int VEC, bool PEERS, bool FUSE>
 __global__ void __launch_bounds__(kThreads)
 csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict__ rowptr, const int *__restrict__ col,
                   const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y, const PeerList<T> peers,
                   int fuse_bands, int band_m, const T *__restrict__ vy)
 {
     // rows [row0, m): the whole matrix in one launch, or one band / row chunk of the pipelined host path.
-    // fuse_bands > 0: these are rows of the LAST band of a band-major copy; the partial sums of the fuse_bands
-    // earlier bands (vy, complete: written by an earlier launch) are folded in here, in band order, and the
-    // final value goes to row (virtual row - fuse_bands*band_m) of y -- band_reduce_kernel without its own pass.
+    // FUSE (pipelined host path only; a separate instantiation so that the plain kernel keeps its 40 registers):
+    // these are rows of the LAST band of a band-major copy; the partial sums of the fuse_bands earlier bands
+    // (vy, complete: written by an earlier launch) are folded in here, in band order, and the final value goes
+    // to row (virtual row - fuse_bands*band_m) of y -- band_reduce_kernel without its own pass.
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long row_l = row0 + gt / TPR;
@@ -209,7 +210,7 @@ csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict_
     if (end - start > long_thr) { valid = false; end = start; }  // hub row: left to the long-row path
     int out_row = row;
     T prev = 0;
-    if (fuse_bands > 0) {
+    if (FUSE) {
         out_row = row - fuse_bands * band_m;
         if (valid && sl == 0) {  // issued before the row walk: in flight while the row is being summed
             prev = ldg_stream(vy + out_row);
@@ -218,7 +219,7 @@ csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict_
     }
     T sum = row_partial<T, VEC>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
     sum = group_sum_c<T, TPR>(sum);
-    if (valid && sl == 0) store_y<PEERS>(y, peers, out_row, fuse_bands > 0 ? prev + sum : sum);
+    if (valid && sl == 0) store_y<PEERS>(y, peers, out_row, FUSE ? prev + sum : sum);
 }
 
 // ------------------------------------------------------------------------------------------------

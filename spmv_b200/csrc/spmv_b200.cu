@@ -721,8 +721,9 @@ static void launch_vector(DeviceState *st, int tpr, int row0, int row1, const T 
     if (grid <= 0) return;
 #define SB_ARGS row0, row1, st->nnz, st->long_thr, st->a_rowptr, st->a_col, (const T *)st->a_val, x, y, peers, fuse_bands, st->m, (const T *)st->v_y
 #define SB_CASE(N) case N: \
-        if (peers.n > 0) csr_vector_kernel<T, N, VEC, true><<<grid, kThreads, 0, st->stream>>>(SB_ARGS); \
-        else csr_vector_kernel<T, N, VEC, false><<<grid, kThreads, 0, st->stream>>>(SB_ARGS); \
+        if (fuse_bands > 0) csr_vector_kernel<T, N, VEC, false, true><<<grid, kThreads, 0, st->stream>>>(SB_ARGS); \
+        else if (peers.n > 0) csr_vector_kernel<T, N, VEC, true, false><<<grid, kThreads, 0, st->stream>>>(SB_ARGS); \
+        else csr_vector_kernel<T, N, VEC, false, false><<<grid, kThreads, 0, st->stream>>>(SB_ARGS); \
         break;
     switch (tpr) { SB_CASE(1) SB_CASE(2) SB_CASE(4) SB_CASE(8) SB_CASE(16) default: SB_CASE(32) }
 #undef SB_CASE
@@ -780,12 +781,9 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
             if (tiles <= 0) continue;
             band_coo_kernel<T><<<tiles, kThreads, 0, s>>>(e0, e1, tile_base, st->coo_row, st->coo_col, (const T *)st->coo_val, x, y_out,
                                                          (T *)st->carry_val, st->carry_row);
+            carry_fixup_kernel<T><<<blocks_for(tiles), kThreads, 0, s>>>(tiles, st->carry_row + tile_base, (const T *)st->carry_val + tile_base, y_out);
             tile_base += tiles;
-            count_launch();
-        }
-        if (tile_base > 0) {
-            carry_fixup_kernel<T><<<blocks_for(tile_base), kThreads, 0, s>>>(tile_base, st->carry_row, (const T *)st->carry_val, y_out);
-            count_launch();
+            count_launch(2);
         }
         if (st->n_peers > 0) {
             PeerList<T> pr;
