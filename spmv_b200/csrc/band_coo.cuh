@@ -129,7 +129,9 @@ band_coo_kernel(int e0, int e1, int tile_base, const int *__restrict__ brow, con
     // the writes follow at the end.
     T old[kCooIpt];
 #pragma unroll
-    for (int k = 0; k < kCooIpt; ++k) old[k] = out_row[k] >= 0 ? y[out_row[k]] : (T)0;
+    for (int k = 0; k < kCooIpt; ++k) old[k] = out_row[k] >= 0 ? y[out_row[k]] : (T)0;  // default caching: neighbours share sectors
+    // (evict-first / no-allocate hints on this sweep measured 30 % slower: the 4 rows of a sector are touched by
+    // different lanes at different times and would be fetched from DRAM again)
 
     int ex_key, agg_key;
     T ex_val, agg_val;

@@ -272,7 +272,12 @@ static bool build_band_major(DeviceState *st)
             // and banding only pays when the accesses are NOT already diagonal-local
             if (k <= kMaxBands && st->far_fraction > 0.25) {
                 if ((double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
-                else if (opt("coo_bands") == 0) st->coo_bands = (int)k;  // too sparse for virtual rows: COO bands
+                else if (opt("coo_bands") == 0) {
+                    // too sparse for virtual rows: COO bands.  Every band costs one read-modify-write sweep over
+                    // y, so fewer and fuller slices win here (C5 shard: 32 bands 7.4 ms, 46 bands 7.7 ms)
+                    const long long kc = (long long)ceil(xbytes / usable);
+                    st->coo_bands = (int)(kc < 2 ? 2 : kc);
+                }
             }
         }
     }
@@ -1091,7 +1096,7 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
         xd = st->x_stage;
     }
     if (!y_dev) yd = st->y_stage;
-    if (st->x_window && xd != st->window_base && xb) {
+    if (st->x_window && xd != st->window_base && xb && st->kernel != SPMV_B200_KERNEL_BAND_COO) {
         // optional: mark x as persisting for everything launched on this stream
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
