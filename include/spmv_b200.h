@@ -37,7 +37,7 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
 /* ---- options (process-global, read when a handle is created) --------------------------------------
  * Also settable through the environment as SPMV_B200_<KEY IN CAPITALS>.  Keys:
  *   "sell_sigma"      sorting window of Method_SellCSigma (multiple of 32, <= 4096; default 256)
- *   "csr5_sigma"      nnz per lane of a CSR5 tile (4, 8 or 16; default 0 = 8 on diagonal-local matrices, else 16)
+ *   "csr5_sigma"      nnz per lane of a CSR5 tile (4, 8 or 16; default 0 = 16, or 8 below 2^25 non-zeros)
  *   "block_nnz"       nnz per row block of Method_Balanced (default 512)
  *   "tile_items"      items per thread of the merge-path / equal-nnz tiles (4..16; default 8)
  *   "tpr"             force threads-per-row of Method_Parallel (power of two <= 32; 0 = from mean)

@@ -194,7 +194,7 @@ csr5_kernel(int p, int bit_y, int bit_ss, const uint32_t *__restrict__ tile_ptr,
     const bool tile_starts_row = (__shfl_sync(kFull, flags, 0) >> 31) & 1;
     const long long base = (long long)t * kC5Omega * SIGMA;
 
-    // all 2*SIGMA coalesced streaming loads first, then the gathers
+    // all 2*SIGMA coalesced streaming loads first ...
     int c[SIGMA];
     T v[SIGMA];
 #pragma unroll
@@ -202,11 +202,17 @@ csr5_kernel(int p, int bit_y, int bit_ss, const uint32_t *__restrict__ tile_ptr,
 #pragma unroll
     for (int i = 0; i < SIGMA; ++i) v[i] = ldg_stream(tval + base + i * kC5Omega + lane, pf);
 
+    // ... and ALL gathers before the first use: v[i] becomes the product a_ij * x_j.  The segmented sums below
+    // store finished rows as they go; with the gathers inside that loop every row end would expose one full
+    // gather latency (the store needs the running sum, the next gather is issued behind the store).
+#pragma unroll
+    for (int i = 0; i < SIGMA; ++i) v[i] = v[i] * ldg_x(x + c[i], pl);
+
     if (row_start == row_stop) {
         // fast track (csr5_spmv_avx2.h:7-49): the whole tile lies inside one row
         T sum = 0;
 #pragma unroll
-        for (int i = 0; i < SIGMA; ++i) sum = fma_t(v[i], ldg_x(x + c[i], pl), sum);
+        for (int i = 0; i < SIGMA; ++i) sum += v[i];
         sum = group_sum_c<T, 32>(sum);
         if (lane == 0) {
             if (tile_starts_row) { stg_y(y + row_start, sum); carry_row[t] = -1; }
@@ -234,7 +240,7 @@ csr5_kernel(int p, int bit_y, int bit_ss, const uint32_t *__restrict__ tile_ptr,
                 ++next_idx;
             }
         }
-        sum = fma_t(v[i], ldg_x(x + c[i], pl), sum);
+        sum += v[i];
     }
     if (!seen) { first_sum = sum; sum = 0; }
 

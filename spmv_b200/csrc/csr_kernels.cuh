@@ -238,6 +238,7 @@ __device__ __forceinline__ void row_block_body(int r0, int r1, int lane, int nnz
 {
     constexpr int rows_per_iter = 32 / TPR;
     const int sub = lane / TPR, sl = lane & (TPR - 1);
+    // (staging the block's row pointers with one coalesced load + shuffles was measured: no gain, C4 0.72 -> 0.69)
     for (int base = r0; base < r1; base += rows_per_iter) {
         const int row = base + sub;
         const bool valid = row < r1;

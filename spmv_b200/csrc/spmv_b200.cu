@@ -480,8 +480,8 @@ static bool build_sell(DeviceState *st)
 template <typename T>
 static bool build_csr5(DeviceState *st)
 {
-    int sigma = (int)opt("csr5_sigma");  // 0 = automatic: 8 on diagonal-local matrices (fewer registers, more warps in flight)
-    if (sigma != 4 && sigma != 8 && sigma != 16) sigma = (st->far_fraction >= 0.0 && st->far_fraction <= 0.25) ? 8 : 16;
+    int sigma = (int)opt("csr5_sigma");  // 0 = automatic: 16, or 8 on small matrices (twice the tiles to fill the GPU)
+    if (sigma != 4 && sigma != 8 && sigma != 16) sigma = st->nnz < (1 << 25) ? 8 : 16;
     st->c5_sigma = sigma;
     // anonymouslib_avx2.h:124-146 at omega = 32
     int base = 2, by = 1;
