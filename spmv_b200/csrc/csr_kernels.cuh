@@ -270,11 +270,12 @@ row_block_kernel(int parts, int nnz, const int *__restrict__ splitter, const int
     // lanes per row from the block's own mean row length (warp-uniform): compile-time bodies so that the row
     // walk unrolls and the butterfly has a fixed depth
 #define SB_BODY(N) row_block_body<T, VEC, PEERS, N>(r0, r1, lane, nnz4, rowptr, col, val, x, y, peers, pl, pf)
-    if (avg <= 4) SB_BODY(1);
-    else if (avg <= 8) SB_BODY(2);
-    else if (avg <= 16) SB_BODY(4);
-    else if (avg <= 32) SB_BODY(8);
-    else if (avg <= 64) SB_BODY(16);
+    constexpr int per_lane = VEC == 4 ? 7 : 4;  // batches of 8 per lane (mode 4) / one 4-element chunk per lane
+    if (avg <= per_lane) SB_BODY(1);
+    else if (avg <= 2 * per_lane) SB_BODY(2);
+    else if (avg <= 4 * per_lane) SB_BODY(4);
+    else if (avg <= 8 * per_lane) SB_BODY(8);
+    else if (avg <= 16 * per_lane) SB_BODY(16);
     else SB_BODY(32);
 #undef SB_BODY
 }
