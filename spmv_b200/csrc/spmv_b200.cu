@@ -52,7 +52,7 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"rb_auto", 0},     {"coo_bands", 0}};
+                                       {"coo_bands", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -218,8 +218,7 @@ static void resolve_load_mode(DeviceState *st)
     if (!forced) mode = 4;
     if (mode == 1 && !st->aligned) mode = 2;
     st->load_mode = (int)mode;
-    // the row-block kernel (run-time lanes per row): aligned chunks unless told otherwise
-    st->rb_mode = (forced && mode < 3) ? (int)mode : ((st->aligned && opt("rb_auto") == 0) ? 1 : st->load_mode);
+    st->rb_mode = st->load_mode;  // the row-block kernel reads the streams the same way (C4 0.71 -> 0.77 in mode 4)
 }
 
 static int pick_tpr(long long nnz, int m)
