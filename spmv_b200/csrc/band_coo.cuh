@@ -91,12 +91,9 @@ band_coo_kernel(int e0, int e1, int tile_base, const int *__restrict__ brow, con
 #pragma unroll
     for (int k = 0; k < kCooIpt; ++k) {
         const int i = tid + k * kThreads;
-        if (i < cnt) {
-            const int j = t0 + i;
-            s_row[pad8(i)] = ldg_stream(brow + j, pf);
-            s_prod[pad8(i)] = ldg_stream(bval + j, pf) * ldg_x(x + ldg_stream(bcol + j, pf), pl);
-        }
+        if (i < cnt) s_row[pad8(i)] = ldg_stream(brow + t0 + i, pf);
     }
+    tile_products<T, kCooIpt>(tid, t0, cnt, bcol, bval, x, pl, s_prod);
     // the row that follows the tile inside this band (-1: the band ends here, the last segment is closed)
     if (tid == 0) s_row[pad8(cnt)] = (t0 + cnt < e1) ? brow[t0 + cnt] : -1;
     __syncthreads();

@@ -13,6 +13,37 @@ namespace sb {
 // distinct banks (stride 9 elements)
 __device__ __forceinline__ int pad8(int i) { return i + (i >> 3); }
 
+// Products of a tile's slice of the non-zero stream into shared memory: element i = tid + k*kThreads of the
+// tile (coalesced).  Three separate passes -- all ColIdx / Val loads, then all x gathers, then the stores -- so
+// that a thread has its 2*IPT stream loads and then its IPT gathers in flight together instead of one dependent
+// round trip per element (the inline-asm loads keep their program order).
+template <typename T, int IPT>
+__device__ __forceinline__ void tile_products(int tid, int first, int count, const int *__restrict__ col,
+                                              const T *__restrict__ val, const T *__restrict__ x, uint64_t pl,
+                                              T *__restrict__ s_prod)
+{
+    int c[IPT];
+    T v[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int i = tid + k * kThreads;
+        c[k] = i < count ? ldg_stream(col + first + i) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int i = tid + k * kThreads;
+        v[k] = i < count ? ldg_stream(val + first + i) : (T)0;
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+        if (c[k] >= 0) v[k] = v[k] * ldg_x(x + c[k], pl);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int i = tid + k * kThreads;
+        if (i < count) s_prod[pad8(i)] = v[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Precomputation (handle construction)
 // ------------------------------------------------------------------------------------------------
@@ -122,14 +153,7 @@ merge_path_kernel(int m, int nnz, const int2 *__restrict__ coords, const int *__
         s_rowend[i] = rowptr[r < m ? r : m];
     }
     // products, coalesced over the tile's slice of the non-zero stream
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const int i = tid + k * kThreads;
-        if (i < tile_nz) {
-            const int j = nz0 + i;
-            s_prod[pad8(i)] = ldg_stream(val + j) * ldg_x(x + ldg_stream(col + j), pl);
-        }
-    }
+    tile_products<T, IPT>(tid, nz0, tile_nz, col, val, x, pl, s_prod);
     __syncthreads();
 
     // this thread's start on the tile-local merge path
@@ -215,12 +239,7 @@ nnz_split_kernel(int m, int nnz, const int *__restrict__ tile_rows, const int *_
     int r_last = tile_rows[t + 1];
     if (r_last > m - 1) r_last = m - 1;
 
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const int i = tid + k * kThreads;
-        const int j = tile_start + i;
-        if (j < tile_end) s_prod[pad8(i)] = ldg_stream(val + j) * ldg_x(x + ldg_stream(col + j), pl);
-    }
+    tile_products<T, IPT>(tid, tile_start, tile_end - tile_start, col, val, x, pl, s_prod);
     if (tid == 0) carry_row[t] = -1;
     __syncthreads();
 
