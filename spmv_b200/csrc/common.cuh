@@ -88,6 +88,8 @@ struct DeviceState {
     int2 *merge_coords = nullptr;   // merge-path: (row, nnz) start of each tile [tiles+1]
     void *carry_val = nullptr;      // [tiles] partial sum that belongs to a row started earlier
     int *carry_row = nullptr;       // [tiles] that row, or -1
+    void *carry2_val = nullptr;     // level-2 carry list of the two-level fix-up: 2 entries per group of 64 tiles
+    int *carry2_row = nullptr;
     // Method_SellCSigma
     int sigma = 0, banner = 0, slices = 0, sell_variant = 0;
     long long padded = 0;

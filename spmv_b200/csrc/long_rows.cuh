@@ -71,10 +71,23 @@ long_seg_kernel(int n_segs, const int *__restrict__ seg_row, const int *__restri
     const int b = start[i] + (seg - seg_ptr[i]) * kLongSeg;
     const int row_end = rowptr[row[i] + 1];
     const int e = (row_end - b > kLongSeg) ? b + kLongSeg : row_end;
+    // predicated batches of 8 per lane: 16 stream loads, then 8 gathers in flight together (a plain loop costs two
+    // dependent round trips per element: measured 420 us -> see DESIGN.md for 35 M hub entries of C3)
+    constexpr int B = 8;
     T acc = 0;
-#pragma unroll 4
-    for (int j = b + lane; j < e; j += 32)
-        acc = fma_t(ldg_stream(val + j, pf), ldg_x(x + ldg_stream(col + j, pf), pl), acc);
+    for (int j0 = b + lane; j0 < e; j0 += 32 * B) {
+        int c[B];
+        T v[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) c[k] = (j0 + 32 * k < e) ? ldg_stream(col + j0 + 32 * k, pf) : -1;
+#pragma unroll
+        for (int k = 0; k < B; ++k) v[k] = (j0 + 32 * k < e) ? ldg_stream(val + j0 + 32 * k, pf) : (T)0;
+        T part = 0;
+#pragma unroll
+        for (int k = 0; k < B; ++k)
+            if (c[k] >= 0) part = fma_t(v[k], ldg_x(x + c[k], pl), part);
+        acc += part;
+    }
     acc = group_sum_c<T, 32>(acc);
     if (lane == 0) partial[seg] = acc;
 }

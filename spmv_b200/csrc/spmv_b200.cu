@@ -141,6 +141,8 @@ static void free_layouts(DeviceState *st)
     dfree(st->merge_coords); st->merge_coords = nullptr;
     dfree(st->carry_val); st->carry_val = nullptr;
     dfree(st->carry_row); st->carry_row = nullptr;
+    dfree(st->carry2_val); st->carry2_val = nullptr;
+    dfree(st->carry2_row); st->carry2_row = nullptr;
     dfree(st->sell_perm); st->sell_perm = nullptr;
     dfree(st->sell_width); st->sell_width = nullptr;
     dfree(st->sell_full); st->sell_full = nullptr;
@@ -327,6 +329,31 @@ static bool build_splitter(DeviceState *st, int m, const int *rowptr, int parts,
     return true;
 }
 
+// carry arrays of the tile kernels: one (row, value) per tile + the level-2 list of the two-level fix-up
+static bool alloc_carries(DeviceState *st, int tiles)
+{
+    const size_t t = tiles > 0 ? (size_t)tiles : 1;
+    const size_t g2 = 2 * ((t + kCarryGroup - 1) / kCarryGroup);
+    return SB_CUDA(cudaMalloc(&st->carry_val, t * st->vsize)) && dmalloc(&st->carry_row, t) &&
+           SB_CUDA(cudaMalloc(&st->carry2_val, g2 * st->vsize)) && dmalloc(&st->carry2_row, g2);
+}
+
+// y[row] += the carries of `tiles` consecutive tiles, in tile order; long lists in two levels
+template <typename T>
+static void launch_carry_fixup(DeviceState *st, cudaStream_t s, int tiles, const int *carry_row, const T *carry_val, T *y)
+{
+    if (tiles <= 0) return;
+    if (tiles < 16 * kCarryGroup) {
+        carry_fixup_kernel<T><<<blocks_for(tiles), kThreads, 0, s>>>(tiles, carry_row, carry_val, y);
+        count_launch();
+        return;
+    }
+    const int groups = (tiles + kCarryGroup - 1) / kCarryGroup;
+    carry_group_kernel<T><<<blocks_for(groups), kThreads, 0, s>>>(tiles, carry_row, carry_val, y, st->carry2_row, (T *)st->carry2_val);
+    carry_fixup_kernel<T><<<blocks_for(2 * groups), kThreads, 0, s>>>(2 * groups, st->carry2_row, (const T *)st->carry2_val, y);
+    count_launch(2);
+}
+
 // Segment list for the entries the main kernel does not cover: covered[r] leading entries of row r are done
 // by the main kernel, the rest by long_seg_kernel / long_final_kernel (long_rows.cuh).  Frees `covered`.
 static bool build_long_rows(DeviceState *st, int *covered, bool accumulate)
@@ -413,8 +440,7 @@ static bool build_tiles(DeviceState *st, bool merge)
             st->tiles, (int)per_tile, st->nnz, st->a_m, st->a_rowptr, st->tile_rows);
     }
     SB_TRY(cudaGetLastError());
-    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)st->tiles * st->vsize))) return false;
-    if (!dmalloc(&st->carry_row, (size_t)st->tiles)) return false;
+    if (!alloc_carries(st, st->tiles)) return false;
     st->kernel = merge ? SPMV_B200_KERNEL_MERGE_PATH : SPMV_B200_KERNEL_NNZ_SPLIT;
     return true;
 }
@@ -528,9 +554,7 @@ static bool build_csr5(DeviceState *st)
     c5_transpose_kernel<T><<<blocks_for(st->nnz), kThreads, 0, st->stream>>>(
         st->nnz, sigma, p, st->c5_tile_ptr, st->a_col, (const T *)st->a_val, st->c5_col, (T *)st->c5_val);
     SB_TRY(cudaGetLastError());
-    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)p * sizeof(T)))) return false;
-    if (!dmalloc(&st->carry_row, (size_t)p)) return false;
-    return true;
+    return alloc_carries(st, p);
 }
 
 // COO column bands (band_coo.cuh): stable bucketing of the CSR entries by col / band_cols
@@ -571,8 +595,7 @@ static bool build_band_coo(DeviceState *st)
     st->coo_tiles = 0;
     for (int b = 0; b < K; ++b) st->coo_tiles += ceil_div((long long)st->coo_ptr[b + 1] - st->coo_ptr[b], kCooTile);
     st->tiles = st->coo_tiles;
-    if (!SB_CUDA(cudaMalloc(&st->carry_val, (size_t)(st->coo_tiles ? st->coo_tiles : 1) * sizeof(T)))) return false;
-    if (!dmalloc(&st->carry_row, (size_t)st->coo_tiles)) return false;
+    if (!alloc_carries(st, st->coo_tiles)) return false;
     st->kernel = SPMV_B200_KERNEL_BAND_COO;
     return true;
 }
@@ -771,9 +794,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     cudaStream_t s = st->stream;
     if (st->m == 0) return true;
     if (st->kernel == SPMV_B200_KERNEL_NONE) {  // nnz == 0: y = 0
-        fill_zero_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out);
-        count_launch();
-        return SB_CUDA(cudaGetLastError());
+        return SB_CUDA(cudaMemsetAsync(y_out, 0, (size_t)st->m * sizeof(T), s));  // all-zero bits = +0.0
     }
     if (st->kernel == SPMV_B200_KERNEL_BAND_COO) {
         // y = 0, then one launch per band (ascending: each adds its segment sums to y), then the carries
@@ -785,9 +806,9 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
             if (tiles <= 0) continue;
             band_coo_kernel<T><<<tiles, kThreads, 0, s>>>(e0, e1, tile_base, st->coo_row, st->coo_col, (const T *)st->coo_val, x, y_out,
                                                          (T *)st->carry_val, st->carry_row);
-            carry_fixup_kernel<T><<<blocks_for(tiles), kThreads, 0, s>>>(tiles, st->carry_row + tile_base, (const T *)st->carry_val + tile_base, y_out);
+            launch_carry_fixup<T>(st, s, tiles, st->carry_row + tile_base, (const T *)st->carry_val + tile_base, y_out);
             tile_base += tiles;
-            count_launch(2);
+            count_launch();
         }
         if (st->n_peers > 0) {
             PeerList<T> pr;
@@ -841,8 +862,8 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
             merge_path_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         else
             merge_path_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->merge_coords, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
-        carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
-        count_launch(2);
+        launch_carry_fixup<T>(st, s, st->tiles, st->carry_row, (const T *)st->carry_val, y);
+        count_launch();
         break;
     }
     case SPMV_B200_KERNEL_NNZ_SPLIT: {
@@ -850,8 +871,8 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
             nnz_split_kernel<T, 4><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
         else
             nnz_split_kernel<T, 8><<<st->tiles, kThreads, 0, s>>>(m, st->nnz, st->tile_rows, st->a_rowptr, st->a_col, val, x, y, (T *)st->carry_val, st->carry_row);
-        carry_fixup_kernel<T><<<blocks_for(st->tiles), kThreads, 0, s>>>(st->tiles, st->carry_row, (const T *)st->carry_val, y);
-        count_launch(2);
+        launch_carry_fixup<T>(st, s, st->tiles, st->carry_row, (const T *)st->carry_val, y);
+        count_launch();
         break;
     }
     case SPMV_B200_KERNEL_SELL: {
@@ -879,8 +900,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     case SPMV_B200_KERNEL_CSR5: {
         const int p = st->c5_p;
         if (st->has_empty_rows) {
-            fill_zero_kernel<T><<<blocks_for(m), kThreads, 0, s>>>(m, y);
-            count_launch();
+            if (!SB_CUDA(cudaMemsetAsync(y, 0, (size_t)m * sizeof(T), s))) return false;  // all-zero bits = +0.0
         }
         const T *tval = (const T *)st->c5_val;
         if (p > 1) {
@@ -893,8 +913,8 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         const int tail_nz0 = (p - 1) * kC5Omega * st->c5_sigma;
         csr5_tail_kernel<T><<<blocks_for((long long)(m - st->c5_tail_start) * 32), kThreads, 0, s>>>(
             m, st->c5_tail_start, tail_nz0, p - 1, st->a_rowptr, st->c5_col, tval, x, y, (T *)st->carry_val, st->carry_row);
-        carry_fixup_kernel<T><<<blocks_for(p), kThreads, 0, s>>>(p, st->carry_row, (const T *)st->carry_val, y);
-        count_launch(2);
+        launch_carry_fixup<T>(st, s, p, st->carry_row, (const T *)st->carry_val, y);
+        count_launch();
         break;
     }
     default:

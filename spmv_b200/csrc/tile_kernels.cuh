@@ -256,8 +256,15 @@ nnz_split_kernel(int m, int nnz, const int *__restrict__ tile_rows, const int *_
         int rs = 0, re = 0;
         if (valid) { rs = rowptr[row]; re = rowptr[row + 1]; }
         const int lo = max(rs, tile_start), hi = min(re, tile_end);
-        T sum = 0;
-        for (int j = lo + sl; j < hi; j += tpr) sum += s_prod[pad8(j - tile_start)];
+        // blocked: a row much longer than the tile's mean is walked by few lanes, and a plain chain of hundreds of
+        // adds would exceed the 8*eps*sum|a x| bound (seen on R-MAT at full size: 12.8 eps)
+        T sum = 0, blk = 0;
+        int in_blk = 0;
+        for (int j = lo + sl; j < hi; j += tpr) {
+            blk += s_prod[pad8(j - tile_start)];
+            if (++in_blk == 32) { sum += blk; blk = 0; in_blk = 0; }
+        }
+        sum += blk;
         sum = group_sum(sum, tpr);
         if (valid && sl == 0) {
             if (rs < tile_start) {
@@ -289,6 +296,45 @@ __global__ void carry_fixup_kernel(int tiles, const int *__restrict__ carry_row,
     T acc = carry_val[t];
     for (int u = t + 1; u < tiles && carry_row[u] == row; ++u) acc += carry_val[u];
     y[row] += acc;
+}
+
+// Two-level variant for long carry chains (a hub row of 2.5 M non-zeros is 4900 CSR5 tiles: one thread walking
+// that chain costs ~70 us and piles up rounding error).  Level 1: a thread sums the runs inside its group of
+// kCarryGroup consecutive tiles; runs that lie wholly inside the group are added to y at once, the group's first
+// and last run -- which may continue in the neighbouring groups -- go to a list of 2 entries per group, on which
+// carry_fixup_kernel then runs as before (chains 64x shorter).  Same order every time: bitwise reproducible.
+constexpr int kCarryGroup = 64;
+
+template <typename T>
+__global__ void carry_group_kernel(int tiles, const int *__restrict__ carry_row, const T *__restrict__ carry_val,
+                                   T *__restrict__ y, int *__restrict__ g_row, T *__restrict__ g_val)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int u0 = g * kCarryGroup;
+    if (u0 >= tiles) return;
+    const int u1 = min(u0 + kCarryGroup, tiles);
+    int cur = -1, head_row = -1, runs = 0;
+    T acc = 0, head_val = 0;
+    for (int u = u0; u < u1; ++u) {
+        const int r = carry_row[u];
+        const T v = carry_val[u];
+        if (r == cur) { acc += v; continue; }
+        if (cur >= 0) {  // the run of row `cur` is complete inside this group
+            if (runs == 0) { head_row = cur; head_val = acc; } else y[cur] += acc;
+            ++runs;
+        }
+        cur = r;
+        acc = v;
+    }
+    // the last run may continue in the next group; a group that is ONE run keeps its row in both slots (value
+    // once) so that the level-2 chain of that row has no gap
+    int tail_row = cur;
+    T tail_val = acc;
+    if (cur >= 0 && runs == 0) { head_row = cur; head_val = acc; tail_val = 0; }
+    g_row[2 * g] = head_row;
+    g_val[2 * g] = head_val;
+    g_row[2 * g + 1] = tail_row;
+    g_val[2 * g + 1] = tail_val;
 }
 
 }  // namespace sb

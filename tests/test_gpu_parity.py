@@ -349,3 +349,27 @@ def test_coo_band_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
         api.set_option("coo_bands", 0)
     assert h.kernel == "band_coo" and h.struct.spmvMethod == api.Method_Balanced2
     h.destroy()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+def test_mega_hub_rows_two_level_carries(libpath, port, serial_ref, dt):
+    """Rows of 2.3 M and 0.4 M non-zeros: thousands of consecutive tiles carry into one row, which takes the
+    two-level carry fix-up (carry_group_kernel) in the merge-path / equal-nnz / CSR5 kernels and the long-row
+    path in Method_Parallel / SELL.  The 8*eps*sum|a x| bound must still hold against the exact sum."""
+    a = M.from_row_lengths([5] * 200 + [2_300_000] + [0] * 5 + [7] * 300 + [400_000] + [2] * 100, 50_000).astype(dt)
+    x = M.make_x(a.n, 13, dt)
+    for method in METHODS:
+        if method == api.Method_Serial:
+            continue  # the reference-order chain is checked on the other cases; here it only costs time
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+        y = np.full(a.m, np.nan, dtype=dt)
+        h.spmv(x, y)
+        tag = f"mega_hub/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
+        assert not np.isnan(y).any(), tag
+        check_y(port, serial_ref, a, x, y, method, tag)
+        y2 = np.full(a.m, np.nan, dtype=dt)
+        h.spmv(x, y2)
+        assert bits_equal(y, y2), tag
+        if h.kernel in ("merge_path", "nnz_split", "csr5"):
+            assert h.info("tiles") >= 16 * 64, tag  # long enough for the two-level path
+        h.destroy()
