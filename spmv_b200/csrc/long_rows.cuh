@@ -24,6 +24,19 @@ __global__ void long_cover_threshold_kernel(int m, int row0, int thr, const int 
     if (r >= row0) covered[r] = len > thr ? 0 : len;
 }
 
+// non-zeros that sit in rows of at most thr entries (integer counter, builder only)
+__global__ void short_nnz_kernel(int m, int thr, const int *__restrict__ rowptr, unsigned long long *__restrict__ out)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (r < m) {
+        const int len = rowptr[r + 1] - rowptr[r];
+        if (len <= thr) v = (unsigned long long)len;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 __global__ void long_count_kernel(int m, const int *__restrict__ rowptr, const int *__restrict__ covered,
                                   int *__restrict__ cnt_rows, int *__restrict__ cnt_segs)
 {
@@ -61,8 +74,10 @@ __global__ void __launch_bounds__(kThreads)
 long_seg_kernel(int n_segs, const int *__restrict__ seg_row, const int *__restrict__ row,
                 const int *__restrict__ start, const int *__restrict__ seg_ptr, const int *__restrict__ rowptr,
                 const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
-                T *__restrict__ partial)
+                T *__restrict__ partial, T *__restrict__ y, int finish_single, int accumulate)
 {
+    // finish_single: a row with ONE segment is finished right here (its sole writer at this point of the stream)
+    // and long_final_kernel skips it -- most SELL overflow rows are of that kind
     const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
     const int seg = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -89,19 +104,28 @@ long_seg_kernel(int n_segs, const int *__restrict__ seg_row, const int *__restri
         acc += part;
     }
     acc = group_sum_c<T, 32>(acc);
-    if (lane == 0) partial[seg] = acc;
+    if (lane == 0) {
+        if (finish_single && seg_ptr[i + 1] - seg_ptr[i] == 1) {
+            const int r = row[i];
+            stg_y(y + r, accumulate ? y[r] + acc : acc);
+        } else {
+            partial[seg] = acc;
+        }
+    }
 }
 
 // one warp per long row: y[row] = (accumulate ? y[row] : 0) + sum of its segment sums, in segment order
 template <typename T, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
-long_final_kernel(int n_rows, int accumulate, const int *__restrict__ row, const int *__restrict__ seg_ptr,
-                  const T *__restrict__ partial, T *__restrict__ y, const PeerList<T> peers)
+long_final_kernel(int n_rows, int accumulate, int skip_single, const int *__restrict__ row,
+                  const int *__restrict__ seg_ptr, const T *__restrict__ partial, T *__restrict__ y,
+                  const PeerList<T> peers)
 {
     const int i = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (i >= n_rows) return;
     const int s0 = seg_ptr[i], s1 = seg_ptr[i + 1];
+    if (skip_single && s1 - s0 == 1) return;  // finished by long_seg_kernel
     T acc = 0;
     for (int s = s0 + lane; s < s1; s += 32) acc += partial[s];
     acc = group_sum_c<T, 32>(acc);

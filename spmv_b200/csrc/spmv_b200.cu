@@ -343,13 +343,13 @@ template <typename T>
 static void launch_carry_fixup(DeviceState *st, cudaStream_t s, int tiles, const int *carry_row, const T *carry_val, T *y)
 {
     if (tiles <= 0) return;
-    if (tiles < 16 * kCarryGroup) {
+    if (tiles < 1024) {
         carry_fixup_kernel<T><<<blocks_for(tiles), kThreads, 0, s>>>(tiles, carry_row, carry_val, y);
         count_launch();
         return;
     }
     const int groups = (tiles + kCarryGroup - 1) / kCarryGroup;
-    carry_group_kernel<T><<<blocks_for(groups), kThreads, 0, s>>>(tiles, carry_row, carry_val, y, st->carry2_row, (T *)st->carry2_val);
+    carry_group_kernel<T><<<blocks_for((long long)groups * 32), kThreads, 0, s>>>(tiles, carry_row, carry_val, y, st->carry2_row, (T *)st->carry2_val);
     carry_fixup_kernel<T><<<blocks_for(2 * groups), kThreads, 0, s>>>(2 * groups, st->carry2_row, (const T *)st->carry2_val, y);
     count_launch(2);
 }
@@ -389,17 +389,49 @@ static bool build_long_rows(DeviceState *st, int *covered, bool accumulate)
 
 // Method_Parallel: rows longer than ~256 entries per lane would keep one lane group busy long after the rest
 // of the grid has drained; they go to the long-row path as a whole.
-static bool build_long_rows_threshold(DeviceState *st, int tpr)
+static void free_long_rows(DeviceState *st)
+{
+    dfree(st->lr_row); st->lr_row = nullptr;
+    dfree(st->lr_start); st->lr_start = nullptr;
+    dfree(st->lr_seg_ptr); st->lr_seg_ptr = nullptr;
+    dfree(st->lr_seg_row); st->lr_seg_row = nullptr;
+    dfree(st->lr_partial); st->lr_partial = nullptr;
+    st->lr_rows = st->lr_segs = 0;
+}
+
+static bool build_long_rows_at(DeviceState *st, int thr)
+{
+    st->long_thr = thr;
+    int *covered = nullptr;
+    if (!dmalloc(&covered, (size_t)st->a_m + 1)) return false;
+    long_cover_threshold_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, 0, thr, st->a_rowptr, covered);
+    SB_TRY(cudaGetLastError());
+    return build_long_rows(st, covered, /*accumulate=*/false);
+}
+
+static bool build_long_rows_threshold(DeviceState *st)
 {
     long long thr = opt("long_thr");  // 0 = automatic, < 0 = off
     if (thr < 0) { st->long_thr = 0x7fffffff; return true; }
-    if (thr == 0) { thr = 256LL * tpr; if (thr < 512) thr = 512; if (thr > 4096) thr = 4096; }
-    st->long_thr = (int)thr;
-    int *covered = nullptr;
-    if (!dmalloc(&covered, (size_t)st->a_m + 1)) return false;
-    long_cover_threshold_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, 0, st->long_thr, st->a_rowptr, covered);
-    SB_TRY(cudaGetLastError());
-    return build_long_rows(st, covered, /*accumulate=*/false);
+    const bool automatic = thr == 0;
+    if (automatic) { thr = 256LL * st->tpr; if (thr < 512) thr = 512; if (thr > 4096) thr = 4096; }
+    if (!build_long_rows_at(st, (int)thr)) return false;
+    // A short-row matrix WITH hub rows (power-law graphs): the lanes per row came from a mean that the hubs
+    // inflate, and rows of a few hundred entries keep their lane group busy long after its neighbours are done.
+    // Re-split at 128 entries and size the lane groups for the rows that stay (C3: 1.26 -> 1.17 ms).
+    if (automatic && st->lr_rows > 0 && st->tpr <= 4 && opt("tpr") == 0) {
+        unsigned long long *d = nullptr, h = 0;
+        if (!dmalloc(&d, 1)) return false;
+        SB_TRY(cudaMemsetAsync(d, 0, sizeof(*d), st->stream));
+        short_nnz_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, 128, st->a_rowptr, d);
+        SB_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st->stream));
+        SB_TRY(cudaStreamSynchronize(st->stream));
+        dfree(d);
+        free_long_rows(st);
+        st->tpr = pick_tpr((long long)h, st->a_m);
+        return build_long_rows_at(st, 128);
+    }
+    return true;
 }
 
 // Host-pointer pipeline of the CSR-vector kernel (option "pipeline", default on): which prefix of x each of
@@ -620,7 +652,7 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
     case Method_Parallel:
         st->tpr = pick_tpr(st->nnz, st->a_m);
         st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
-        if (!build_long_rows_threshold(st, st->tpr)) return false;
+        if (!build_long_rows_threshold(st)) return false;
         return build_pipeline(st);
     case Method_Balanced:
     case Method_Balanced2: {
@@ -922,11 +954,13 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         return false;
     }
     if (st->lr_rows > 0) {  // hub rows / SELL overflow: segment sums, then one ordered add per row
+        const int single = direct.n == 0;  // with peer destinations every final value goes through long_final_kernel
         long_seg_kernel<T><<<blocks_for((long long)st->lr_segs * 32), kThreads, 0, s>>>(
-            st->lr_segs, st->lr_seg_row, st->lr_row, st->lr_start, st->lr_seg_ptr, st->a_rowptr, st->a_col, val, x, (T *)st->lr_partial);
+            st->lr_segs, st->lr_seg_row, st->lr_row, st->lr_start, st->lr_seg_ptr, st->a_rowptr, st->a_col, val, x, (T *)st->lr_partial,
+            y, single, st->lr_accumulate);
         const int fgrid = blocks_for((long long)st->lr_rows * 32);
-        if (direct.n > 0) long_final_kernel<T, true><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
-        else long_final_kernel<T, false><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
+        if (direct.n > 0) long_final_kernel<T, true><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, single, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
+        else long_final_kernel<T, false><<<fgrid, kThreads, 0, s>>>(st->lr_rows, st->lr_accumulate, single, st->lr_row, st->lr_seg_ptr, (const T *)st->lr_partial, y, direct);
         count_launch(2);
     }
     if (banded) {

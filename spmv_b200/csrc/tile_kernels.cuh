@@ -299,42 +299,47 @@ __global__ void carry_fixup_kernel(int tiles, const int *__restrict__ carry_row,
 }
 
 // Two-level variant for long carry chains (a hub row of 2.5 M non-zeros is 4900 CSR5 tiles: one thread walking
-// that chain costs ~70 us and piles up rounding error).  Level 1: a thread sums the runs inside its group of
-// kCarryGroup consecutive tiles; runs that lie wholly inside the group are added to y at once, the group's first
-// and last run -- which may continue in the neighbouring groups -- go to a list of 2 entries per group, on which
-// carry_fixup_kernel then runs as before (chains 64x shorter).  Same order every time: bitwise reproducible.
-constexpr int kCarryGroup = 64;
+// that chain costs ~70 us and piles up rounding error).  Level 1: a warp takes kCarryGroup = 32 consecutive tiles,
+// one per lane (coalesced), and sums the runs of equal rows with a segmented shuffle scan; runs that lie wholly
+// inside the group are added to y at once, the group's first and last run -- which may continue in the
+// neighbouring groups -- go to a list of 2 entries per group, on which carry_fixup_kernel then runs as before
+// (chains 32x shorter).  Same order every time: bitwise reproducible.
+constexpr int kCarryGroup = 32;
 
 template <typename T>
-__global__ void carry_group_kernel(int tiles, const int *__restrict__ carry_row, const T *__restrict__ carry_val,
-                                   T *__restrict__ y, int *__restrict__ g_row, T *__restrict__ g_val)
+__global__ void __launch_bounds__(kThreads)
+carry_group_kernel(int tiles, const int *__restrict__ carry_row, const T *__restrict__ carry_val,
+                   T *__restrict__ y, int *__restrict__ g_row, T *__restrict__ g_val)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int u0 = g * kCarryGroup;
-    if (u0 >= tiles) return;
-    const int u1 = min(u0 + kCarryGroup, tiles);
-    int cur = -1, head_row = -1, runs = 0;
-    T acc = 0, head_val = 0;
-    for (int u = u0; u < u1; ++u) {
-        const int r = carry_row[u];
-        const T v = carry_val[u];
-        if (r == cur) { acc += v; continue; }
-        if (cur >= 0) {  // the run of row `cur` is complete inside this group
-            if (runs == 0) { head_row = cur; head_val = acc; } else y[cur] += acc;
-            ++runs;
-        }
-        cur = r;
-        acc = v;
+    const int g = (int)(((long long)blockIdx.x * kThreads + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if ((long long)g * kCarryGroup >= tiles) return;
+    const int u = g * kCarryGroup + lane;
+    const int r = u < tiles ? carry_row[u] : -1;
+    T v = (u < tiles && r >= 0) ? carry_val[u] : (T)0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // inclusive sum over the run of equal rows ending at this lane
+        const int r2 = __shfl_up_sync(kFull, r, o);
+        const T v2 = __shfl_up_sync(kFull, v, o);
+        if (lane >= o && r2 == r) v = v2 + v;
     }
-    // the last run may continue in the next group; a group that is ONE run keeps its row in both slots (value
-    // once) so that the level-2 chain of that row has no gap
-    int tail_row = cur;
-    T tail_val = acc;
-    if (cur >= 0 && runs == 0) { head_row = cur; head_val = acc; tail_val = 0; }
-    g_row[2 * g] = head_row;
-    g_val[2 * g] = head_val;
-    g_row[2 * g + 1] = tail_row;
-    g_val[2 * g + 1] = tail_val;
+    const int next = __shfl_down_sync(kFull, r, 1);
+    const bool run_end = lane == 31 || next != r;
+    const int first_row = __shfl_sync(kFull, r, 0), last_row = __shfl_sync(kFull, r, 31);
+    // last lane of the FIRST run: rows are contiguous, so it is the last lane before the first mismatch with lane 0
+    const unsigned same_as_first = __ballot_sync(kFull, r == first_row);
+    const int first_end = (same_as_first == kFull) ? 31 : (__ffs(~same_as_first) - 2);
+    const T head_val = __shfl_sync(kFull, v, first_end);
+    const T last_val = __shfl_sync(kFull, v, 31);
+    if (run_end && r >= 0 && lane > first_end && r != last_row) y[r] += v;  // a run wholly inside the group
+    if (lane == 0) {
+        const bool one_run = first_end == 31;
+        g_row[2 * g] = first_row;
+        g_val[2 * g] = first_row >= 0 ? head_val : (T)0;
+        // a group that is ONE run keeps its row in both slots (value once): the level-2 chain has no gap
+        g_row[2 * g + 1] = last_row;
+        g_val[2 * g + 1] = (one_run || last_row < 0) ? (T)0 : last_val;
+    }
 }
 
 }  // namespace sb

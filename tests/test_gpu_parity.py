@@ -371,5 +371,5 @@ def test_mega_hub_rows_two_level_carries(libpath, port, serial_ref, dt):
         h.spmv(x, y2)
         assert bits_equal(y, y2), tag
         if h.kernel in ("merge_path", "nnz_split", "csr5"):
-            assert h.info("tiles") >= 16 * 64, tag  # long enough for the two-level path
+            assert h.info("tiles") >= 1024, tag  # long enough for the two-level path
         h.destroy()
