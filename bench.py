@@ -39,6 +39,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Native libraries write to file descriptor 1 behind Python's back
+# (NCCL prints its version banner there), so descriptor 1 is pointed at stderr for the whole run and the result
+# line goes to a private duplicate of the original stdout.
+RESULT = None
+
+
+def claim_stdout():
+    global RESULT
+    if RESULT is None:
+        sys.stdout.flush()
+        RESULT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = RESULT if RESULT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
@@ -241,7 +261,7 @@ def run_reference_arm(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,7 +315,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # belt and braces: see RESULT below
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
@@ -466,7 +486,7 @@ def run_gpu_arm(args):
             line["power_method_fused"] = fused
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     for h in handles.values():
         h.destroy()
     A.destroy()
@@ -487,6 +507,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--small", action="store_true", help="64x smaller matrices (script debugging only; not a bench)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference_arm(args)
