@@ -246,10 +246,8 @@ static bool build_band_major(DeviceState *st)
     const double usable = st->dev_l2 > 0 ? 0.5 * (double)st->dev_l2 : 63.0 * 1048576.0;  // random-access reach
     {
         // locality probe: the share of entries further than 1/8 of the L2 reach from the (scaled) diagonal.
-        // It decides two things: whether banding pays (below) and how the CSR kernels read the matrix
-        // streams -- gather-dominated matrices are bound by L2 requests and want the fewest, widest stream
-        // loads (128/256-bit chunks); diagonal-local ones are bound by DRAM and run best with plain scalar
-        // loads through L1 (measured: C1 0.50 -> 0.62, C4 0.69 -> 0.76 of the HBM peak; C2 0.39 -> 0.36).
+        // > 25 % = gather-dominated (bound by L2 requests), else diagonal-local (bound by DRAM).  It decides
+        // whether banding can pay (below) and which SELL kernel flavour runs (build_sell).
         unsigned long long *far = nullptr, h_far = 0;
         if (!dmalloc(&far, 1)) return false;
         SB_TRY(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
@@ -277,7 +275,7 @@ static bool build_band_major(DeviceState *st)
                     // too sparse for virtual rows: COO bands.  Every band costs one read-modify-write sweep over
                     // y, so fewer and fuller slices win here (C5 shard: 32 bands 7.4 ms, 46 bands 7.7 ms)
                     const long long kc = (long long)ceil(xbytes / usable);
-                    st->coo_bands = (int)(kc < 2 ? 2 : kc);
+                    st->coo_bands = (int)(kc < 2 ? 2 : (kc > kMaxBands ? kMaxBands : kc));
                 }
             }
         }
