@@ -211,6 +211,44 @@ merge_path_kernel(int m, int nnz, const int2 *__restrict__ coords, const int *__
     }
 }
 
+// rows r0 .. r_last of one equal-nnz tile, TPR lanes per row, products taken from shared memory
+template <typename T, int TPR>
+__device__ __forceinline__ void nnz_split_rows(int t, int r0, int r_last, int tile_start, int tile_end, int lane, int warp,
+                                               const int *__restrict__ rowptr, const T *__restrict__ s_prod,
+                                               T *__restrict__ y, T *__restrict__ carry_val, int *__restrict__ carry_row)
+{
+    constexpr int groups_per_warp = 32 / TPR;
+    constexpr int stride_rows = kWarpsPerCta * groups_per_warp;
+    const int sub = lane / TPR, sl = lane & (TPR - 1);
+    for (int base = r0; base <= r_last; base += stride_rows) {  // warp-uniform trip count
+        const int row = base + warp * groups_per_warp + sub;
+        const bool valid = row <= r_last;
+        int rs = 0, re = 0;
+        if (valid) { rs = rowptr[row]; re = rowptr[row + 1]; }
+        const int lo = max(rs, tile_start), hi = min(re, tile_end);
+        // blocked: a row much longer than the tile's mean is walked by few lanes, and a plain chain of hundreds of
+        // adds would exceed the 8*eps*sum|a x| bound (seen on R-MAT at full size: 12.8 eps)
+        T sum = 0, blk = 0;
+        int in_blk = 0;
+        for (int j = lo + sl; j < hi; j += TPR) {
+            blk += s_prod[pad8(j - tile_start)];
+            if (++in_blk == 32) { sum += blk; blk = 0; in_blk = 0; }
+        }
+        sum += blk;
+        sum = group_sum_c<T, TPR>(sum);
+        if (valid && sl == 0) {
+            if (rs < tile_start) {
+                // continues a row begun in an earlier tile (only row == r0 can): carry it
+                carry_val[t] = sum;
+                carry_row[t] = row;
+            } else if (rs < tile_end || re == rs) {
+                // row starts in this tile (complete, or its first slice), or is empty
+                if (re > rs || rs >= tile_start) stg_y(y + row, sum);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Method_Balanced_Yid on the GPU: equal-nnz tiles.  Replaces spmv_parallel_balanced_Yid_cpp_{d,s}
 // (reference src/src_spmv/parallel_balanced_Yid_spmv.c:97-225): tile t owns non-zeros
@@ -245,38 +283,16 @@ nnz_split_kernel(int m, int nnz, const int *__restrict__ tile_rows, const int *_
 
     const int nrows = r_last - r0 + 1;
     const int avg = (tile_end - tile_start + nrows - 1) / max(nrows, 1);
-    int tpr = 1;
-    while (tpr < 32 && 2 * tpr < avg) tpr <<= 1;
-    const int groups_per_warp = 32 / tpr;
-    const int sub = lane / tpr, sl = lane & (tpr - 1);
-    const int stride_rows = kWarpsPerCta * groups_per_warp;
-    for (int base = r0; base <= r_last; base += stride_rows) {  // warp-uniform trip count
-        const int row = base + warp * groups_per_warp + sub;
-        const bool valid = row <= r_last;
-        int rs = 0, re = 0;
-        if (valid) { rs = rowptr[row]; re = rowptr[row + 1]; }
-        const int lo = max(rs, tile_start), hi = min(re, tile_end);
-        // blocked: a row much longer than the tile's mean is walked by few lanes, and a plain chain of hundreds of
-        // adds would exceed the 8*eps*sum|a x| bound (seen on R-MAT at full size: 12.8 eps)
-        T sum = 0, blk = 0;
-        int in_blk = 0;
-        for (int j = lo + sl; j < hi; j += tpr) {
-            blk += s_prod[pad8(j - tile_start)];
-            if (++in_blk == 32) { sum += blk; blk = 0; in_blk = 0; }
-        }
-        sum += blk;
-        sum = group_sum(sum, tpr);
-        if (valid && sl == 0) {
-            if (rs < tile_start) {
-                // continues a row begun in an earlier tile (only row == r0 can): carry it
-                carry_val[t] = sum;
-                carry_row[t] = row;
-            } else if (rs < tile_end || re == rs) {
-                // row starts in this tile (complete, or its first slice), or is empty
-                if (re > rs || rs >= tile_start) stg_y(y + row, sum);
-            }
-        }
-    }
+    // lanes per row from the tile's mean row length (CTA-uniform), ~4 products per lane; compile-time bodies so
+    // that the butterfly has a fixed depth and the row walk carries no loop over a run-time lane count
+#define SB_ROWS(N) nnz_split_rows<T, N>(t, r0, r_last, tile_start, tile_end, lane, warp, rowptr, s_prod, y, carry_val, carry_row)
+    if (avg <= 4) SB_ROWS(1);
+    else if (avg <= 8) SB_ROWS(2);
+    else if (avg <= 16) SB_ROWS(4);
+    else if (avg <= 32) SB_ROWS(8);
+    else if (avg <= 64) SB_ROWS(16);
+    else SB_ROWS(32);
+#undef SB_ROWS
 }
 
 // ------------------------------------------------------------------------------------------------
