@@ -62,6 +62,9 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *                     reference's widths (every slice as wide as its longest row)
  *   "long_thr"        Method_Parallel leaves rows longer than this to the long-row path (0 = automatic:
  *                     256 x lanes-per-row clamped to [512, 4096]; < 0 = never)
+ *   "row_bins"        1 (default) = Method_Parallel on short-row matrices that also have hub rows bins the rows by
+ *                     length class (<= 8, <= 32, <= 128 entries: 1, 4, 16 lanes per row, one launch each; longer
+ *                     rows on the long-row path); 0 = one lane-group size for all rows
  *   "pipeline"        1 (default) = spmv() with HOST x and y on a Method_Parallel handle overlaps the PCIe
  *                     copies with the kernels (x in pieces, y in row chunks); 0 = copy, run, copy
  * Returns 0, or -1 for an unknown key. */

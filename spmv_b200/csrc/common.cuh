@@ -96,6 +96,11 @@ struct DeviceState {
     int *sell_perm = nullptr, *sell_width = nullptr, *sell_full = nullptr, *sell_col = nullptr;
     long long *sell_slice_ptr = nullptr;
     void *sell_val = nullptr;
+    // Method_Parallel on short-row matrices with hubs: rows binned by length class (<= 8, <= 32, <= 128), one
+    // launch per bin with 1 / 4 / 16 lanes per row; longer rows are on the long-row list
+    bool binned = false;
+    int *bin_list = nullptr;        // row ids, bin after bin, ascending inside a bin
+    int bin_ptr[4] = {};
     // hyper-sparse column bands as COO lists (band_coo.cuh): x_bands = K but the active view stays the CSR
     int coo_bands = 0, coo_tiles = 0;
     int coo_ptr[kMaxPieces + 1] = {};  // entry range of every band (host copy)

@@ -222,6 +222,38 @@ csr_vector_kernel(int row0, int m, int nnz, int long_thr, const int *__restrict_
     if (valid && sl == 0) store_y<PEERS>(y, peers, out_row, FUSE ? prev + sum : sum);
 }
 
+// The same row walk over a LIST of rows: Method_Parallel on matrices whose rows are short but not uniformly so
+// (power-law graphs).  Rows are binned by length class at create and every bin gets the lanes per row that fit it,
+// so a warp only ever holds rows of similar length (no lane group waiting for a 100-entry neighbour).
+template <typename T, int TPR, bool PEERS>
+__global__ void __launch_bounds__(kThreads)
+csr_vector_list_kernel(int count, int nnz, const int *__restrict__ list, const int *__restrict__ rowptr,
+                       const int *__restrict__ col, const T *__restrict__ val, const T *__restrict__ x,
+                       T *__restrict__ y, const PeerList<T> peers)
+{
+    const uint64_t pl = policy_evict_last(), pf = policy_evict_first();
+    const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long idx = gt / TPR;
+    const int sl = threadIdx.x & (TPR - 1);
+    const bool valid = idx < count;
+    const int row = valid ? list[idx] : 0;
+    const int start = valid ? rowptr[row] : 0;
+    const int end = valid ? rowptr[row + 1] : 0;
+    T sum = row_partial<T, 4>(start, end, sl, TPR, nnz & ~3, col, val, x, pl, pf);
+    sum = group_sum_c<T, TPR>(sum);
+    if (valid && sl == 0) store_y<PEERS>(y, peers, row, sum);
+}
+
+// bin of a row by its length: 0 (<= 8), 1 (<= 32), 2 (<= 128), 3 (longer: long-row path)
+__global__ void row_bin_kernel(int m, const int *__restrict__ rowptr, unsigned char *__restrict__ bin, int *__restrict__ ids)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const int len = rowptr[r + 1] - rowptr[r];
+    bin[r] = (unsigned char)(len <= 8 ? 0 : len <= 32 ? 1 : len <= 128 ? 2 : 3);
+    ids[r] = r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Method_Balanced.  Replaces spmv_parallel_balanced_cpp_{d,s} (reference
 // src/src_spmv/parallel_balanced_spmv.c:77-125): "thread t does rows csrSplitter[t]..csrSplitter[t+1]"

@@ -52,7 +52,7 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"coo_bands", 0}};
+                                       {"coo_bands", 0},    {"row_bins", 1}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -155,6 +155,7 @@ static void free_layouts(DeviceState *st)
     dfree(st->c5_off); st->c5_off = nullptr;
     dfree(st->c5_col); st->c5_col = nullptr;
     dfree(st->c5_val); st->c5_val = nullptr;
+    dfree(st->bin_list); st->bin_list = nullptr;
     dfree(st->coo_row); st->coo_row = nullptr;
     dfree(st->coo_col); st->coo_col = nullptr;
     dfree(st->coo_val); st->coo_val = nullptr;
@@ -414,20 +415,38 @@ static bool build_long_rows_threshold(DeviceState *st)
     const bool automatic = thr == 0;
     if (automatic) { thr = 256LL * st->tpr; if (thr < 512) thr = 512; if (thr > 4096) thr = 4096; }
     if (!build_long_rows_at(st, (int)thr)) return false;
-    // A short-row matrix WITH hub rows (power-law graphs): the lanes per row came from a mean that the hubs
-    // inflate, and rows of a few hundred entries keep their lane group busy long after its neighbours are done.
-    // Re-split at 128 entries and size the lane groups for the rows that stay (C3: 1.26 -> 1.17 ms).
-    if (automatic && st->lr_rows > 0 && st->tpr <= 4 && opt("tpr") == 0) {
-        unsigned long long *d = nullptr, h = 0;
-        if (!dmalloc(&d, 1)) return false;
-        SB_TRY(cudaMemsetAsync(d, 0, sizeof(*d), st->stream));
-        short_nnz_kernel<<<blocks_for(st->a_m), kThreads, 0, st->stream>>>(st->a_m, 128, st->a_rowptr, d);
-        SB_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st->stream));
-        SB_TRY(cudaStreamSynchronize(st->stream));
-        dfree(d);
+    // A short-row matrix WITH hub rows (power-law graphs): one lane-group size for all rows leaves most lanes
+    // waiting for the longest row of their warp.  Bin the rows by length class instead -- stable radix sort of the
+    // row ids by bin -- and give every bin its own launch; rows beyond 128 entries go to the long-row path.
+    // (C3: 1.26 ms with one lane-group size, 1.20 ms re-split at 128 entries, see DESIGN.md for the binned figure)
+    if (automatic && st->lr_rows > 0 && st->tpr <= 4 && opt("tpr") == 0 && opt("row_bins") != 0) {
         free_long_rows(st);
-        st->tpr = pick_tpr((long long)h, st->a_m);
-        return build_long_rows_at(st, 128);
+        if (!build_long_rows_at(st, 128)) return false;
+        const int m = st->a_m;
+        unsigned char *key_in = nullptr, *key_out = nullptr;
+        int *ids = nullptr, *d_ptr = nullptr;
+        void *tmp = nullptr;
+        size_t tmp_bytes = 0;
+        bool ok = dmalloc(&key_in, (size_t)m) && dmalloc(&key_out, (size_t)m) && dmalloc(&ids, (size_t)m) &&
+                  dmalloc(&st->bin_list, (size_t)m) && dmalloc(&d_ptr, 5);
+        if (ok) {
+            row_bin_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->a_rowptr, key_in, ids);
+            ok = SB_CUDA(cudaGetLastError()) &&
+                 SB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, ids, st->bin_list, m, 0, 2, st->stream)) &&
+                 SB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1)) &&
+                 SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, ids, st->bin_list, m, 0, 2, st->stream));
+        }
+        int h_ptr[5] = {0, 0, 0, 0, 0};
+        if (ok) {
+            coo_band_ptr_kernel<<<1, kThreads, 0, st->stream>>>(m, 4, key_out, d_ptr);  // first sorted row of every bin
+            ok = SB_CUDA(cudaGetLastError()) &&
+                 SB_CUDA(cudaMemcpyAsync(h_ptr, d_ptr, sizeof(h_ptr), cudaMemcpyDeviceToHost, st->stream)) &&
+                 SB_CUDA(cudaStreamSynchronize(st->stream));
+        }
+        dfree(key_in); dfree(key_out); dfree(ids); dfree(d_ptr); dfree(tmp);
+        if (!ok) return false;
+        for (int b = 0; b < 4; ++b) st->bin_ptr[b] = h_ptr[b];  // bin b = list[bin_ptr[b], bin_ptr[b+1]); bin 3 is unused
+        st->binned = true;
     }
     return true;
 }
@@ -872,7 +891,22 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         // (one launch over all bands + band_reduce measured faster than two launches with the reduce fused into
         // the last band: 2.59 vs 2.64 ms on C2; the fused form is used by the pipelined host path, where the
         // last band runs in row chunks anyway)
-        launch_vector_mode<T>(st, 0, m, x, y, direct);
+        if (st->binned) {
+            static const int lanes[3] = {1, 4, 16};
+            for (int b = 0; b < 3; ++b) {
+                const int count = st->bin_ptr[b + 1] - st->bin_ptr[b];
+                if (count <= 0) continue;
+                const int grid = blocks_for((long long)count * lanes[b]);
+                const int *list = st->bin_list + st->bin_ptr[b];
+#define SB_BIN(N) if (direct.n > 0) csr_vector_list_kernel<T, N, true><<<grid, kThreads, 0, s>>>(count, st->nnz, list, st->a_rowptr, st->a_col, val, x, y, direct); \
+                  else csr_vector_list_kernel<T, N, false><<<grid, kThreads, 0, s>>>(count, st->nnz, list, st->a_rowptr, st->a_col, val, x, y, direct)
+                if (b == 0) { SB_BIN(1); } else if (b == 1) { SB_BIN(4); } else { SB_BIN(16); }
+#undef SB_BIN
+                count_launch();
+            }
+        } else {
+            launch_vector_mode<T>(st, 0, m, x, y, direct);
+        }
         scattered = scattered || !banded;
         break;
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
@@ -1279,6 +1313,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "csr5_num_offsets") return st->c5_num_offsets;
     if (k == "csr5_tail_start") return st->c5_tail_start;
     if (k == "pipeline") return st->pipeline;
+    if (k == "binned") return st->binned;
     if (k == "long_rows") return st->lr_rows;
     if (k == "long_segs") return st->lr_segs;
     if (k == "long_thr") return st->long_thr;

@@ -126,15 +126,15 @@ def test_parallel_hub_rows_go_to_the_long_row_path(libpath):
     h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
     lens = np.diff(a.rowptr)
     thr = h.info("long_thr")
-    # short rows + hubs: split at 128 entries, lanes per row sized for the rows that stay (mean 2.7 -> 1 lane)
-    assert thr == 128 and h.info("tpr") == 1
+    # short rows + hubs: rows binned by length class (<= 8 / <= 32 / <= 128), hubs beyond 128 on the long-row list
+    assert thr == 128 and h.info("binned") == 1
     assert h.info("long_rows") == int((lens > thr).sum()) == 2
     assert h.info("long_segs") == int(((lens[lens > thr] + 2047) // 2048).sum())
     h.destroy()
     # a matrix without hubs keeps the plain rule: 256 * lanes-per-row clamped to [512, 4096], nothing on the list
     a = all_cases()["uni32"]()
     h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
-    assert h.info("long_thr") == 256 * h.info("tpr") == 2048 and h.info("long_rows") == 0
+    assert h.info("long_thr") == 256 * h.info("tpr") == 2048 and h.info("long_rows") == 0 and h.info("binned") == 0
     h.destroy()
 
 
