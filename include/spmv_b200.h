@@ -65,6 +65,11 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "row_bins"        1 (default) = Method_Parallel on short-row matrices that also have hub rows bins the rows by
  *                     length class (<= 8, <= 32, <= 128 entries: 1, 4, 16 lanes per row, one launch each; longer
  *                     rows on the long-row path); 0 = one lane-group size for all rows
+ *   "pin_host"        1 = a pageable HOST x or y (>= 1 MiB) that is passed to spmv() twice in a row is page-locked
+ *                     in place (cudaHostRegister) so that its copies run at PCIe speed (3x on the reference's
+ *                     sample driver); released when the caller switches buffers and at clear / destroy.  The
+ *                     caller must not free such a buffer while the handle lives.  0 (default) = never touch the
+ *                     caller's pages
  *   "pipeline"        1 (default) = spmv() with HOST x and y on a Method_Parallel handle overlaps the PCIe
  *                     copies with the kernels (x in pieces, y in row chunks); 0 = copy, run, copy
  * Returns 0, or -1 for an unknown key. */

@@ -47,6 +47,7 @@ struct DeviceState {
     bool aligned = true;            // ColIdx / Val of the active view are 32-byte aligned
     int rb_mode = 1;                // the same choice for the row-block kernel
     int load_mode = 1;              // CSR kernels: 1 = aligned 128/256-bit chunk loads, 2 = scalar via L1, 0 = scalar no-L1
+    int dev_sms = 0;
     long long dev_l2 = 0, dev_persist_max = 0, dev_window_max = 0, cur_persist = 0, cur_fetch = 0;
     bool x_window = false;
     const void *window_base = nullptr;
@@ -58,6 +59,13 @@ struct DeviceState {
     void *val = nullptr;
     bool owns_csr = false;
 
+    // pageable host x / y that keep coming back (the reference's drivers reuse one X and one Y for every call) are
+    // page-locked in place after the second sighting, so that the copies run at PCIe speed instead of being
+    // staged by the driver.  Opt-in (option "pin_host" / SPMV_B200_PIN_HOST=1): the caller must not free such a
+    // buffer while the handle lives.  Undone at clear / destroy or when the caller switches buffers
+    struct PinSlot { const void *ptr = nullptr; size_t bytes = 0; int seen = 0; bool registered = false; };
+    PinSlot pin[2];
+    bool pin_host = false;
     // staging for host-side x / y; the pipelined host path (CSR-vector kernel) copies x in pieces on s_in,
     // computes row chunks as soon as their prefix of x has arrived, and returns finished chunks of y on s_out
     void *x_stage = nullptr, *y_stage = nullptr;

@@ -52,7 +52,8 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"coo_bands", 0},    {"row_bins", 1}};
+                                       {"coo_bands", 0},    {"row_bins", 1},
+                                       {"pin_host", 0}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -168,10 +169,38 @@ static void free_layouts(DeviceState *st)
     dfree(st->y_stage); st->y_stage = nullptr;
 }
 
+static void unpin(DeviceState::PinSlot &slot)
+{
+    if (slot.registered && cudaHostUnregister(const_cast<void *>(slot.ptr)) != cudaSuccess) cudaGetLastError();
+    slot = DeviceState::PinSlot();
+}
+
+// see DeviceState::pin
+static void note_host_buffer(DeviceState *st, int which, const void *p, size_t bytes)
+{
+    DeviceState::PinSlot &slot = st->pin[which];
+    if (slot.ptr != p || slot.bytes != bytes) {
+        unpin(slot);
+        slot.ptr = p;
+        slot.bytes = bytes;
+        slot.seen = 1;
+        return;
+    }
+    if (slot.registered || slot.seen < 0 || bytes < (1u << 20)) return;
+    if (++slot.seen < 2) return;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); slot.seen = -1; return; }
+    if (a.type != cudaMemoryTypeUnregistered) { slot.seen = -1; return; }  // already pinned by the caller
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) slot.registered = true;
+    else { cudaGetLastError(); slot.seen = -1; }  // e.g. registered through another handle: leave it alone
+}
+
 static void free_state(DeviceState *st)
 {
     if (!st) return;
     DeviceGuard g(st->device);
+    unpin(st->pin[0]);
+    unpin(st->pin[1]);
     free_layouts(st);
     for (int i = 0; i < kMaxPieces; ++i) if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
     for (int i = 0; i < kPipeChunks; ++i) if (st->ev_out[i]) cudaEventDestroy(st->ev_out[i]);
@@ -191,6 +220,7 @@ static void apply_device_limits(DeviceState *st)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, st->device) != cudaSuccess) { cudaGetLastError(); return; }
+    st->dev_sms = prop.multiProcessorCount;
     st->dev_l2 = prop.l2CacheSize;
     st->dev_persist_max = prop.persistingL2CacheMaxSize;
     st->dev_window_max = prop.accessPolicyMaxWindowSize;
@@ -207,6 +237,7 @@ static void apply_device_limits(DeviceState *st)
     if (cudaDeviceGetLimit(&v, cudaLimitPersistingL2CacheSize) == cudaSuccess) st->cur_persist = (long long)v;
     if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) == cudaSuccess) st->cur_fetch = (long long)v;
     st->x_window = opt("x_window") != 0;
+    st->pin_host = opt("pin_host") != 0;
 }
 
 // How the CSR kernels read ColIdx / Val.  Option "vec": -1 = automatic, 4 = predicated batches of 8 scalar
@@ -1169,6 +1200,10 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
     const void *xd = Vector_Val_X;
     void *yd = Vector_Val_Y;
     const size_t xb = (size_t)st->n * st->vsize, yb = (size_t)st->m * st->vsize;
+    if (st->pin_host) {
+        if (!x_dev && xb) note_host_buffer(st, 0, Vector_Val_X, xb);
+        if (!y_dev && yb) note_host_buffer(st, 1, Vector_Val_Y, yb);
+    }
     if (!x_dev && !st->x_stage && !SB_CUDA(cudaMalloc(&st->x_stage, xb ? xb : 1))) return;
     if (!y_dev && !st->y_stage && !SB_CUDA(cudaMalloc(&st->y_stage, yb ? yb : 1))) return;
     if (!x_dev && !y_dev && st->pipeline && st->n_peers == 0 && st->kernel == SPMV_B200_KERNEL_CSR_VECTOR && xb && yb) {
