@@ -1349,6 +1349,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "csr5_tail_start") return st->c5_tail_start;
     if (k == "pipeline") return st->pipeline;
     if (k == "binned") return st->binned;
+    if (k == "pinned_host_buffers") return (int)st->pin[0].registered + (int)st->pin[1].registered;
     if (k == "long_rows") return st->lr_rows;
     if (k == "long_segs") return st->lr_segs;
     if (k == "long_thr") return st->long_thr;

@@ -373,3 +373,35 @@ def test_mega_hub_rows_two_level_carries(libpath, port, serial_ref, dt):
         if h.kernel in ("merge_path", "nnz_split", "csr5"):
             assert h.info("tiles") >= 1024, tag  # long enough for the two-level path
         h.destroy()
+
+
+def test_pin_host_option_page_locks_recurring_buffers(libpath, port, serial_ref):
+    """Option pin_host (off by default): pageable x / y that come back on consecutive calls are page-locked in
+    place after the second sighting, released when the caller switches buffers; results do not change."""
+    a = M.laplacian2d(400)  # x, y = 1.28 MB each (>= 1 MiB)
+    x = M.make_x(a.n, 3, np.float64)
+    h0 = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+    y0 = np.empty(a.m)
+    for _ in range(3):
+        h0.spmv(x, y0)
+    assert h0.info("pinned_host_buffers") == 0  # default: the caller's pages are never touched
+    h0.destroy()
+    api.set_option("pin_host", 1)
+    try:
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+    finally:
+        api.set_option("pin_host", 0)
+    y = np.full(a.m, np.nan)
+    h.spmv(x, y)
+    assert h.info("pinned_host_buffers") == 0 and bits_equal(y, y0)
+    y.fill(np.nan)
+    h.spmv(x, y)
+    assert h.info("pinned_host_buffers") == 2 and bits_equal(y, y0)
+    y.fill(np.nan)
+    h.spmv(x, y)
+    assert bits_equal(y, y0)
+    y_other = np.full(a.m, np.nan)      # a different y: the old registration is dropped
+    h.spmv(x, y_other)
+    assert h.info("pinned_host_buffers") == 1 and bits_equal(y_other, y0)
+    check_y(port, serial_ref, a, x, y_other, api.Method_SellCSigma, "pin_host")
+    h.destroy()                         # unregisters x before the arrays go away
