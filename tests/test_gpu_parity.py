@@ -405,3 +405,45 @@ def test_pin_host_option_page_locks_recurring_buffers(libpath, port, serial_ref)
     assert h.info("pinned_host_buffers") == 1 and bits_equal(y_other, y0)
     check_y(port, serial_ref, a, x, y_other, api.Method_SellCSigma, "pin_host")
     h.destroy()                         # unregisters x before the arrays go away
+
+
+def test_spmv_is_cuda_graph_capturable(libpath):
+    """Device-pointer spmv() is a pure sequence of stream-ordered launches on the handle's stream, so an iterated
+    loop can be captured once and replayed (launch-bound small matrices): same bits as direct calls."""
+    import torch
+    dev = torch.device("cuda:0")
+    for name, method, bands in (("lap48", api.Method_Parallel, 0), ("hub", api.Method_Balanced2, 0),
+                                ("uni32", api.Method_SellCSigma, 3), ("skew", api.Method_CSR5SPMV, 0),
+                                ("hub", api.Method_Parallel, 0), ("uni32", api.Method_Balanced_Yid, 0)):
+        a = CASES[name]()
+        if a.m != a.n:
+            continue
+        api.set_option("x_bands", bands)
+        try:
+            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
+        finally:
+            api.set_option("x_bands", 0)
+        x0 = torch.from_numpy(M.make_x(a.n, 8, np.float64) / 64.0).to(dev)
+        # direct: three power iterations x <- A x (ping-pong buffers)
+        xa, xb = x0.clone(), torch.empty_like(x0)
+        for _ in range(3):
+            h.spmv(xa, xb)
+            xa, xb = xb, xa
+        h.sync()
+        want = xa.clone()
+        # captured: the same three calls recorded once on a side stream, replayed twice from the same start
+        side = torch.cuda.Stream()
+        h.set_stream(side.cuda_stream)
+        ga, gb = x0.clone(), torch.empty_like(x0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            h.spmv(ga, gb)
+            h.spmv(gb, ga)
+            h.spmv(ga, gb)
+        for _ in range(2):
+            ga.copy_(x0)
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(gb, want), (name, api.METHOD_NAMES[method])
+        h.set_stream(0)
+        h.destroy()
