@@ -58,6 +58,7 @@ struct DeviceState {
     int *rowptr = nullptr, *col = nullptr;
     void *val = nullptr;
     bool owns_csr = false;
+    bool released_csr = false;      // the upload was freed after a re-laid-out copy took over
 
     // pageable host x / y that keep coming back (the reference's drivers reuse one X and one Y for every call) are
     // page-locked in place after the second sighting, so that the copies run at PCIe speed instead of being

@@ -815,6 +815,15 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
     const bool ok = st->vsize == 8 ? build_method<double>(st, h, method) : build_method<float>(st, h, method);
     if (!ok) return false;
     SB_TRY(cudaStreamSynchronize(st->stream));
+    // Our own upload of the CSR is dead weight once every kernel of the handle reads a re-laid-out copy (the
+    // band-major copy or the COO bands): give those gigabytes back (an adopted device CSR is the caller's).
+    if (st->owns_csr && (st->kernel == SPMV_B200_KERNEL_BAND_COO || st->a_rowptr != st->rowptr)) {
+        dfree(st->rowptr); dfree(st->col); dfree(st->val);
+        st->rowptr = st->col = nullptr;
+        st->val = nullptr;
+        st->owns_csr = false;
+        st->released_csr = true;
+    }
     return true;
 }
 
@@ -1361,6 +1370,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "far_permille") return (long long)(st->far_fraction * 1000.0);
     if (k == "active_rows") return st->a_m;
     if (k == "owns_csr") return st->owns_csr;
+    if (k == "released_csr") return st->released_csr;
     if (k == "vec_ok") return st->load_mode == 1;
     if (k == "load_mode") return st->load_mode;
     if (k == "dev_l2_bytes") return st->dev_l2;

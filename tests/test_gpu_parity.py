@@ -199,6 +199,8 @@ def test_band_major_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
             finally:
                 api.set_option("x_bands", 0)
             assert h.info("x_bands") == (1 if method == api.Method_Serial else bands)
+            # the uploaded CSR is given back once every kernel of the handle reads the band-major copy
+            assert h.info("released_csr") == (0 if method == api.Method_Serial else 1)
             y = np.full(a.m, np.nan, dtype=dt)
             h.spmv(x, y)
             tag = f"bands{bands}/{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
@@ -321,6 +323,7 @@ def test_coo_band_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
                 assert h.kernel == "csr_reforder" and h.info("coo_bands") == 0
             else:
                 assert h.kernel == "band_coo" and h.info("coo_bands") == bands and h.info("x_bands") == bands, tag
+                assert h.info("released_csr") == 1, tag
             y = np.full(a.m, np.nan, dtype=dt)
             h.spmv(x, y)
             assert not np.isnan(y).any(), tag
