@@ -12,6 +12,10 @@ separate leg on the SQUARE C2 matrix row-sharded over the N GPUs (strong scaling
 with an in-place NCCL all-gather timed apart from the SpMV ("power_method") and once with the all-gather
 fused into the SpMV epilogue as NVLink peer stores ("power_method_fused").
 
+Other workloads (`--workload c1|c3|c4|c5|c5shard`) time the remaining BASELINE.json configurations the same way;
+`c5shard` is one GPU's share of C5 at 8 GPUs (2^25 rows x 2^28 columns) on a single GPU.  `--also` names further
+methods timed after the primary one (default: balanced2, sell); their numbers land in "methods".
+
 One JSON line on stdout (rank 0).  `value` = whole-job GFLOP/s with everything resident in HBM;
 `e2e` = the same metric through the C-ABI with HOST x / y (pinned), H2D + kernel + D2H inside the timed
 region; `roofline` = algorithmic bytes (B_min) / kernel time vs the measured HBM copy peak.
