@@ -16,6 +16,18 @@
  *       silent no-op (reference common.c:285).
  *   spmv_clear_handle / spmv_destory_handle (sic)  free the device state (and the handle).
  *
+ * Deviations a client can observe (everything else follows the reference):
+ *   - the matrix VALUES are snapshotted at create (the reference re-reads the caller's arrays on every call for
+ *     Serial / Parallel / Balanced*): after changing Matrix_Val, clear and re-create the handle
+ *     (spmv_b200_info(h, "values_snapshotted") == 1 says so);
+ *   - fp32 Method_CSR5SPMV is a real CSR5 and handle->spmvMethod stays Method_CSR5SPMV (the reference runs SELL and
+ *     stores Method_SellCSigma, common.c:177-180);
+ *   - ONE spmv() in flight per handle: the handle owns staging buffers, partial-sum arrays and events, so calls on
+ *     the same handle must not overlap (different handles are independent);
+ *   - a pageable HOST x or y of at least 1 MiB that is passed twice in a row is page-locked in place so that its
+ *     copies run at PCIe speed, and released when the caller switches buffers or clears / destroys the handle:
+ *     do not free such a buffer while the handle is alive (SPMV_B200_PIN_HOST=0 switches this off).
+ *
  * All functions return void like the reference; failures (CUDA errors, no device) are reported on
  * stderr, latched in spmv_b200_last_error() and leave the handle in a state where spmv() is a no-op.
  * There is no CPU fallback.

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SPMV_B200_VERSION 100 /* round 1 */
+#define SPMV_B200_VERSION 200 /* round 2 */
 
 /* ---- errors ------------------------------------------------------------------------------------
  * The reference swallows every error (common.c:136,285; csr5_spmv.cpp:31-35).  Same void API here,
@@ -44,9 +44,10 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "x_bands"         column bands of the band-major layout that keeps the gathered slice of x inside L2
  *                     (0 = automatic from n and the L2 size, 1 = off, 2..64 forced); every method except
  *                     Method_Serial can run on the band-major copy
- *   "coo_bands"       column bands stored as COO lists sorted by row, for matrices whose bands would hold fewer than
- *                     4 non-zeros per row (0 = automatic, -1 = never, 2..64 forced); replaces the kernel of every
- *                     method except Method_Serial
+ *   "seg_bands"       column bands stored as band segments (entry lists sorted by row inside a band, segment sums
+ *                     merged per row in a second pass), for matrices whose bands would hold fewer than 4 non-zeros
+ *                     per row (0 = automatic, -1 = never, 2..64 forced); replaces the kernel of every method except
+ *                     Method_Serial
  *   "l2_persist"      bytes of L2 set aside for persisting lines at create (0 = leave, -1 = device max)
  *   "l2_fetch"        cudaLimitMaxL2FetchGranularity at create (0 = leave; 32 / 64 / 128)
  *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
@@ -65,11 +66,11 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *   "row_bins"        1 (default) = Method_Parallel on short-row matrices that also have hub rows bins the rows by
  *                     length class (<= 8, <= 32, <= 128 entries: 1, 4, 16 lanes per row, one launch each; longer
  *                     rows on the long-row path); 0 = one lane-group size for all rows
- *   "pin_host"        1 = a pageable HOST x or y (>= 1 MiB) that is passed to spmv() twice in a row is page-locked
- *                     in place (cudaHostRegister) so that its copies run at PCIe speed (3x on the reference's
- *                     sample driver); released when the caller switches buffers and at clear / destroy.  The
- *                     caller must not free such a buffer while the handle lives.  0 (default) = never touch the
- *                     caller's pages
+ *   "pin_host"        1 (default) = a pageable HOST x or y (>= 1 MiB) that is passed to spmv() twice in a row is
+ *                     page-locked in place (cudaHostRegister) so that its copies run at PCIe speed (3x on the
+ *                     reference's sample driver, which reuses one X and one Y for every call); released when the
+ *                     caller switches buffers and at clear / destroy.  The caller must not free such a buffer while
+ *                     the handle lives.  0 = never touch the caller's pages
  *   "pipeline"        1 (default) = spmv() with HOST x and y on a Method_Parallel handle overlaps the PCIe
  *                     copies with the kernels (x in pieces, y in row chunks); 0 = copy, run, copy
  * Returns 0, or -1 for an unknown key. */
@@ -98,8 +99,8 @@ enum {
     SPMV_B200_KERNEL_NNZ_SPLIT = 5,    /* Method_Balanced_Yid */
     SPMV_B200_KERNEL_SELL = 6,         /* Method_SellCSigma */
     SPMV_B200_KERNEL_CSR5 = 7,         /* Method_CSR5SPMV */
-    SPMV_B200_KERNEL_BAND_COO = 8      /* any method but Method_Serial when x needs so many column bands that
-                                          they are hyper-sparse (see "coo_bands") */
+    SPMV_B200_KERNEL_BAND_SEG = 8      /* any method but Method_Serial when x needs so many column bands that
+                                          they are hyper-sparse (see "seg_bands") */
 };
 SPMV_B200_API long long spmv_b200_info(spmv_Handle_t handle, const char *key);
 SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst, size_t dst_bytes);
@@ -137,6 +138,24 @@ SPMV_B200_API int spmv_b200_set_y_peers(spmv_Handle_t handle, int count, void *c
 SPMV_B200_API int spmv_b200_ipc_export(const void *device_ptr, void *handle_out_64);
 SPMV_B200_API void *spmv_b200_ipc_open(const void *handle_64);
 SPMV_B200_API int spmv_b200_ipc_close(void *opened_ptr);
+
+/* ---- column stages: an SpMV in pieces, for overlapping the y -> x exchange of an iterated loop with compute ------
+ * A handle whose layout is banded by columns (the band-major copy of Method_Parallel, or band segments) computes the
+ * contribution of every column band separately and folds them at the end.  These entry points expose that: band b
+ * only reads x[col_lo, col_hi), so in x <- A x on several GPUs a rank can start on the bands whose slice of the new
+ * x has already arrived while the rest is still in flight over NVLink (spmv_b200/multigpu.py: PipelinedPowerMethod).
+ *   spmv_b200_bands         number of column bands that can be staged (1: not banded -- use spmv());
+ *   spmv_b200_band_columns  the half-open column range band `band` reads;
+ *   spmv_b200_spmv_bands    enqueue the partial products of bands [band_first, band_first + band_count) on the
+ *                           handle's stream (x: DEVICE pointer to the full-length vector; any order, each band once);
+ *   spmv_b200_spmv_finish   enqueue the fold: y (DEVICE pointer) = sum over all bands, in band order -- bit for bit
+ *                           the y that spmv() writes, whatever order the bands were staged in; extra destinations
+ *                           set with spmv_b200_set_y_peers are written here.
+ * All return 0, or -1 (not stageable / bad arguments; spmv_b200_last_error()). */
+SPMV_B200_API int spmv_b200_bands(spmv_Handle_t handle);
+SPMV_B200_API int spmv_b200_band_columns(spmv_Handle_t handle, int band, long long *col_lo, long long *col_hi);
+SPMV_B200_API int spmv_b200_spmv_bands(spmv_Handle_t handle, int band_first, int band_count, const void *x_device);
+SPMV_B200_API int spmv_b200_spmv_finish(spmv_Handle_t handle, void *y_device);
 
 /* ---- device memory helpers for C clients (Python clients use torch tensors) ----------------------- */
 SPMV_B200_API void *spmv_b200_malloc(size_t bytes);

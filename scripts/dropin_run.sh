@@ -15,8 +15,8 @@ cd /tmp/dropin
 echo "# nproc=$T; columns: matrix,method,vectorized,threads,nnz,err,pre_ms,avg_ms,GFLOPS_avg,GFLOPS_best" > $OLDPWD/gpurun_out/dropin_c1.csv
 echo "# --- reference library (CPU) ---" >> $OLDPWD/gpurun_out/dropin_c1.csv
 $OLDPWD/oracle/_ref/test_spmv_ref lap1024.mtx $T $T >> $OLDPWD/gpurun_out/dropin_c1.csv
-echo "# --- libspmv_b200.so (B200), pageable X / Y staged by the CUDA driver ---" >> $OLDPWD/gpurun_out/dropin_c1.csv
+echo "# --- libspmv_b200.so (B200), default settings (the driver's recurring X / Y are page-locked in place) ---" >> $OLDPWD/gpurun_out/dropin_c1.csv
 $OLDPWD/oracle/_ref/test_spmv_b200 lap1024.mtx $T $T >> $OLDPWD/gpurun_out/dropin_c1.csv
-echo "# --- libspmv_b200.so (B200), SPMV_B200_PIN_HOST=1: the driver's X / Y page-locked in place ---" >> $OLDPWD/gpurun_out/dropin_c1.csv
-SPMV_B200_PIN_HOST=1 $OLDPWD/oracle/_ref/test_spmv_b200 lap1024.mtx $T $T >> $OLDPWD/gpurun_out/dropin_c1.csv
+echo "# --- libspmv_b200.so (B200), SPMV_B200_PIN_HOST=0: pageable X / Y staged by the CUDA driver ---" >> $OLDPWD/gpurun_out/dropin_c1.csv
+SPMV_B200_PIN_HOST=0 $OLDPWD/oracle/_ref/test_spmv_b200 lap1024.mtx $T $T >> $OLDPWD/gpurun_out/dropin_c1.csv
 cat $OLDPWD/gpurun_out/dropin_c1.csv

@@ -26,7 +26,7 @@ METHOD_NAMES = ["Method_Serial", "Method_Parallel", "Method_Balanced", "Method_B
                 "Method_BalancedYid", "Method_SellCSigma", "Method_Csr5Spmv"]
 
 KERNEL_NAMES = {0: "none", 1: "csr_reforder", 2: "csr_vector", 3: "row_blocks", 4: "merge_path",
-                5: "nnz_split", 6: "sell", 7: "csr5", 8: "band_coo"}
+                5: "nnz_split", 6: "sell", 7: "csr5", 8: "band_seg"}
 
 # every symbol include/spmv.h and include/spmv_b200.h declare
 EXPORTED_FUNCTIONS = [
@@ -37,7 +37,8 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_free", "spmv_b200_memcpy", "spmv_b200_gen_laplacian2d", "spmv_b200_gen_stencil27",
     "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free",
     "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close",
-    "spmv_b200_recommend_method"]
+    "spmv_b200_recommend_method", "spmv_b200_bands", "spmv_b200_band_columns", "spmv_b200_spmv_bands",
+    "spmv_b200_spmv_finish"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -106,6 +107,10 @@ def lib() -> C.CDLL:
     L.spmv_b200_ipc_open.argtypes = [C.c_char_p]
     L.spmv_b200_ipc_open.restype = vp
     L.spmv_b200_ipc_close.argtypes = [vp]
+    L.spmv_b200_bands.argtypes = [spmv_Handle_t]
+    L.spmv_b200_band_columns.argtypes = [spmv_Handle_t, i, C.POINTER(ll), C.POINTER(ll)]
+    L.spmv_b200_spmv_bands.argtypes = [spmv_Handle_t, i, i, vp]
+    L.spmv_b200_spmv_finish.argtypes = [spmv_Handle_t, vp]
     P = C.POINTER(DeviceCSR)
     L.spmv_b200_gen_laplacian2d.argtypes = [i, i, ul, P]
     L.spmv_b200_gen_stencil27.argtypes = [i, i, i, ul, P]
@@ -133,6 +138,10 @@ def _addr(a):
 
 def last_error() -> str:
     return lib().spmv_b200_last_error().decode()
+
+
+def clear_error() -> None:
+    lib().spmv_b200_clear_error()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -211,6 +220,24 @@ class Handle:
         arr = (C.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
         if lib().spmv_b200_set_y_peers(self.h, len(ptrs), arr) != 0:
             raise ValueError("set_y_peers: at most 8 destinations")
+
+    def bands(self) -> int:
+        """Column bands that can be staged one by one (1: use spmv())."""
+        return int(lib().spmv_b200_bands(self.h))
+
+    def band_columns(self, band: int):
+        lo, hi = C.c_longlong(), C.c_longlong()
+        if lib().spmv_b200_band_columns(self.h, band, C.byref(lo), C.byref(hi)) != 0:
+            raise IndexError(band)
+        return int(lo.value), int(hi.value)
+
+    def spmv_bands(self, first: int, count: int, x):
+        if lib().spmv_b200_spmv_bands(self.h, first, count, _addr(x)) != 0:
+            raise RuntimeError("spmv_b200_spmv_bands: " + last_error())
+
+    def spmv_finish(self, y):
+        if lib().spmv_b200_spmv_finish(self.h, _addr(y)) != 0:
+            raise RuntimeError("spmv_b200_spmv_finish: " + last_error())
 
     def set_stream(self, cuda_stream: int):
         lib().spmv_b200_set_stream(self.h, cuda_stream)

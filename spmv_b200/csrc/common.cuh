@@ -51,6 +51,7 @@ struct DeviceState {
     long long dev_l2 = 0, dev_persist_max = 0, dev_window_max = 0, cur_persist = 0, cur_fetch = 0;
     bool x_window = false;
     const void *window_base = nullptr;
+    int layout_fallbacks = 0;       // optional layouts (band copy, band segments, row bins) that could not be built
     int n_peers = 0;                // spmv_b200_set_y_peers
     void *peers[kMaxPeers] = {};
 
@@ -72,7 +73,7 @@ struct DeviceState {
     void *x_stage = nullptr, *y_stage = nullptr;
     bool pipeline = false;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[kMaxPieces] = {}, ev_out[kPipeChunks] = {}, ev_start = nullptr;
+    cudaEvent_t ev_in[kMaxPieces] = {}, ev_out[kPipeChunks] = {}, ev_start = nullptr, ev_x = nullptr;
     int chunk_xmax[kPipeChunks] = {};
 
     // Method_Parallel
@@ -110,11 +111,25 @@ struct DeviceState {
     bool binned = false;
     int *bin_list = nullptr;        // row ids, bin after bin, ascending inside a bin
     int bin_ptr[4] = {};
-    // hyper-sparse column bands as COO lists (band_coo.cuh): x_bands = K but the active view stays the CSR
-    int coo_bands = 0, coo_tiles = 0;
-    int coo_ptr[kMaxPieces + 1] = {};  // entry range of every band (host copy)
-    int *coo_row = nullptr, *coo_col = nullptr;
-    void *coo_val = nullptr;
+    // hyper-sparse column bands as band segments (band_seg.cuh): x_bands = K but the active view stays the CSR
+    int coo_bands = 0, coo_tiles = 0;  // (option / info key names kept from round 1: "coo_bands")
+    int seg_ptr[kMaxPieces + 1] = {};  // first slot of every band in seg_col / seg_val (aligned to 4), [K] = end
+    int seg_cnt[kMaxPieces] = {};      // entries of every band
+    int seg_tile0[kMaxPieces + 1] = {};  // first tile of every band
+    long long seg_total = 0;           // segments = (band, row) pairs with at least one entry
+    int seg_groups = 0;                // 32-row groups of the merge pass
+    int seg_ctas = 0;                  // persistent CTAs per SM of pass 1
+    int seg_grid = 0;                  // persistent CTAs of pass 1 (device-wide occupancy, set at the first launch)
+    bool seg_cross = false;            // some segment crosses a tile boundary: the carry fix-up is needed
+    bool seg_mask64 = false;           // K > 32: 64-bit row masks
+    int *seg_col = nullptr;            // column index | segment-end bit 31
+    void *seg_ent_val = nullptr;       // values, band-major
+    void *seg_mask = nullptr;          // per row: bands in which it has a segment
+    int4 *seg_tile_ent = nullptr;      // per tile: (first slot, entries, L2-prefetch duty: first x element, elements)
+    int *seg_tile_seg0 = nullptr;      // per 256-entry chunk of a tile (8 per tile): index of its first segment sum
+    int *seg_gbase = nullptr;          // [seg_groups][K]: position of a row group's first segment sum in band b's list
+    int *seg_ticket = nullptr;         // ticket counter of pass 1's dynamic tile schedule
+    void *seg_sums = nullptr;          // [seg_total] segment sums, band-major (written by pass 1, read by pass 2)
     // long rows / row tails left over by the main kernel of Method_Parallel and Method_SellCSigma (long_rows.cuh)
     int long_thr = 0x7fffffff;      // CSR-vector kernels skip rows longer than this
     int lr_rows = 0, lr_segs = 0;

@@ -17,7 +17,7 @@
 #include "sell.cuh"
 #include "csr5.cuh"
 #include "long_rows.cuh"
-#include "band_coo.cuh"
+#include "band_seg.cuh"
 
 namespace sb {
 
@@ -52,8 +52,8 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"coo_bands", 0},    {"row_bins", 1},
-                                       {"pin_host", 0}};
+                                       {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},    {"row_bins", 1},
+                                       {"pin_host", 1}};
     std::map<std::string, bool> user_set;
 };
 static Options &options()
@@ -157,9 +157,14 @@ static void free_layouts(DeviceState *st)
     dfree(st->c5_col); st->c5_col = nullptr;
     dfree(st->c5_val); st->c5_val = nullptr;
     dfree(st->bin_list); st->bin_list = nullptr;
-    dfree(st->coo_row); st->coo_row = nullptr;
-    dfree(st->coo_col); st->coo_col = nullptr;
-    dfree(st->coo_val); st->coo_val = nullptr;
+    dfree(st->seg_col); st->seg_col = nullptr;
+    dfree(st->seg_ent_val); st->seg_ent_val = nullptr;
+    dfree(st->seg_mask); st->seg_mask = nullptr;
+    dfree(st->seg_tile_ent); st->seg_tile_ent = nullptr;
+    dfree(st->seg_tile_seg0); st->seg_tile_seg0 = nullptr;
+    dfree(st->seg_gbase); st->seg_gbase = nullptr;
+    dfree(st->seg_ticket); st->seg_ticket = nullptr;
+    dfree(st->seg_sums); st->seg_sums = nullptr;
     dfree(st->lr_row); st->lr_row = nullptr;
     dfree(st->lr_start); st->lr_start = nullptr;
     dfree(st->lr_seg_ptr); st->lr_seg_ptr = nullptr;
@@ -205,6 +210,7 @@ static void free_state(DeviceState *st)
     for (int i = 0; i < kMaxPieces; ++i) if (st->ev_in[i]) cudaEventDestroy(st->ev_in[i]);
     for (int i = 0; i < kPipeChunks; ++i) if (st->ev_out[i]) cudaEventDestroy(st->ev_out[i]);
     if (st->ev_start) cudaEventDestroy(st->ev_start);
+    if (st->ev_x) cudaEventDestroy(st->ev_x);
     if (st->s_in) cudaStreamDestroy(st->s_in);
     if (st->s_out) cudaStreamDestroy(st->s_out);
     if (st->owns_csr) { dfree(st->rowptr); dfree(st->col); dfree(st->val); }
@@ -281,14 +287,16 @@ static bool build_band_major(DeviceState *st)
         // > 25 % = gather-dominated (bound by L2 requests), else diagonal-local (bound by DRAM).  It decides
         // whether banding can pay (below) and which SELL kernel flavour runs (build_sell).
         unsigned long long *far = nullptr, h_far = 0;
-        if (!dmalloc(&far, 1)) return false;
-        SB_TRY(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
-        const int halfwidth = (int)(0.125 * usable / st->vsize);
-        band_locality_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(
-            st->m, (double)st->n / st->m, halfwidth, st->rowptr, st->col, far);
-        SB_TRY(cudaMemcpyAsync(&h_far, far, sizeof(h_far), cudaMemcpyDeviceToHost, st->stream));
-        SB_TRY(cudaStreamSynchronize(st->stream));
+        bool probed = dmalloc(&far, 1) && SB_CUDA(cudaMemsetAsync(far, 0, sizeof(*far), st->stream));
+        if (probed) {
+            const int halfwidth = (int)(0.125 * usable / st->vsize);
+            band_locality_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(
+                st->m, (double)st->n / st->m, halfwidth, st->rowptr, st->col, far);
+            probed = SB_CUDA(cudaMemcpyAsync(&h_far, far, sizeof(h_far), cudaMemcpyDeviceToHost, st->stream)) &&
+                     SB_CUDA(cudaStreamSynchronize(st->stream));
+        }
         dfree(far);
+        if (!probed) return false;  // a 8-byte allocation or a trivial kernel failed: the device is unusable
         st->far_fraction = (double)h_far / (double)st->nnz;
         resolve_load_mode(st);
     }
@@ -296,23 +304,23 @@ static bool build_band_major(DeviceState *st)
         bands = 1;
         // x up to ~1.2x the reach still gathers at >= 85 % of the L2 rate (profiles/r01_gather_probe.txt) and
         // banding costs 15-20 % (virtual row pointers, partial y): R-MAT s24 fp32 (x = 64 MiB) measured 7-15 %
-        // FASTER unbanded, uniform fp64 (x = 128 MiB) 1.9x faster banded
-        if (xbytes > 1.2 * usable) {
-            long long k = (long long)ceil(xbytes / (0.75 * usable));
-            // hyper-sparse bands (< 4 entries per virtual row) cost more in row pointers than they save,
-            // and banding only pays when the accesses are NOT already diagonal-local
-            if (k <= kMaxBands && st->far_fraction > 0.25) {
-                if ((double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
-                else if (opt("coo_bands") == 0) {
-                    // too sparse for virtual rows: COO bands.  Every band costs one read-modify-write sweep over
-                    // y, so fewer and fuller slices win here (C5 shard: 32 bands 7.4 ms, 46 bands 7.7 ms)
-                    const long long kc = (long long)ceil(xbytes / usable);
-                    st->coo_bands = (int)(kc < 2 ? 2 : (kc > kMaxBands ? kMaxBands : kc));
-                }
+        // FASTER unbanded, uniform fp64 (x = 128 MiB) 1.9x faster banded.  Banding only pays when the accesses
+        // are NOT already diagonal-local.
+        if (xbytes > 1.2 * usable && st->far_fraction > 0.25) {
+            const long long k = (long long)ceil(xbytes / (0.75 * usable));
+            if (k <= kMaxBands && (double)st->nnz / ((double)k * st->m) >= 4.0) bands = k;
+            else if (opt("seg_bands") == 0) {
+                // hyper-sparse bands (< 4 entries per virtual row) would cost more in row pointers than they save:
+                // band segments (band_seg.cuh).  More bands = a smaller slice of x = fewer L2 misses of the gathers,
+                // but more and shorter segments for the merge pass.  Measured on the C5 shard (x = 2 GiB, 16 per
+                // row; scripts/c5_sweep.sh): 32 bands 5.24 ms, 40: 4.94, 44: 4.88, 48: 4.78, 52: 4.92, 56: 4.96,
+                // 64: 5.19 -- a slice of about 2/3 of the reach
+                const long long kc = (long long)ceil(xbytes / (0.68 * usable));
+                st->coo_bands = (int)(kc < 2 ? 2 : (kc > kSegMaxBands ? kSegMaxBands : kc));
             }
         }
     }
-    if (opt("coo_bands") >= 2) { st->coo_bands = (int)(opt("coo_bands") > kMaxBands ? kMaxBands : opt("coo_bands")); bands = 1; }
+    if (opt("seg_bands") >= 2) { st->coo_bands = (int)(opt("seg_bands") > kSegMaxBands ? kSegMaxBands : opt("seg_bands")); bands = 1; }
     if (bands <= 1) return true;
     if (bands > kMaxBands) bands = kMaxBands;
     if ((long long)st->m * bands > 0x7fffffffLL - 8192) return true;
@@ -320,19 +328,34 @@ static bool build_band_major(DeviceState *st)
     const int band_cols = (int)(((long long)st->n + K - 1) / K);
     const size_t vm = (size_t)m * K;
     int *counts = nullptr;
-    if (!dmalloc(&counts, vm + 1) || !dmalloc(&st->v_rowptr, vm + 1 + 8) || !dmalloc(&st->v_col, (size_t)st->nnz + 8)) return false;
-    if (!SB_CUDA(cudaMalloc(&st->v_val, ((size_t)st->nnz + 8) * sizeof(T)))) return false;
-    if (!SB_CUDA(cudaMalloc(&st->v_y, vm * sizeof(T)))) return false;
-    SB_TRY(cudaMemsetAsync(counts + vm, 0, sizeof(int), st->stream));
-    band_count_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, counts);
-    SB_TRY(cudaGetLastError());
-    const bool ok = exclusive_scan(counts, st->v_rowptr, (int)vm + 1, st->stream);
+    // The band-major copy is a speed-up only: when it cannot be allocated (or built) the handle keeps running the
+    // plain CSR view it already holds -- never fail a handle over an optional layout.
+    auto give_up = [&]() {
+        cudaGetLastError();
+        dfree(counts);
+        dfree(st->v_rowptr); st->v_rowptr = nullptr;
+        dfree(st->v_col); st->v_col = nullptr;
+        dfree(st->v_val); st->v_val = nullptr;
+        dfree(st->v_y); st->v_y = nullptr;
+        spmv_b200_clear_error();
+        st->layout_fallbacks++;
+        return true;
+    };
+    if (!dmalloc(&counts, vm + 1) || !dmalloc(&st->v_rowptr, vm + 1 + 8) || !dmalloc(&st->v_col, (size_t)st->nnz + 8) ||
+        !SB_CUDA(cudaMalloc(&st->v_val, ((size_t)st->nnz + 8) * sizeof(T))) || !SB_CUDA(cudaMalloc(&st->v_y, vm * sizeof(T))))
+        return give_up();
+    bool ok = SB_CUDA(cudaMemsetAsync(counts + vm, 0, sizeof(int), st->stream));
+    if (ok) {
+        band_count_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, counts);
+        ok = SB_CUDA(cudaGetLastError()) && exclusive_scan(counts, st->v_rowptr, (int)vm + 1, st->stream);
+    }
+    if (ok) {
+        band_scatter_kernel<T><<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, (const T *)st->val,
+                                                                           st->v_rowptr, st->v_col, (T *)st->v_val);
+        ok = SB_CUDA(cudaGetLastError()) && SB_CUDA(cudaStreamSynchronize(st->stream));
+    }
+    if (!ok) return give_up();
     dfree(counts);
-    if (!ok) return false;
-    band_scatter_kernel<T><<<blocks_for(m), kThreads, 0, st->stream>>>(m, K, band_cols, st->rowptr, st->col, (const T *)st->val,
-                                                                       st->v_rowptr, st->v_col, (T *)st->v_val);
-    SB_TRY(cudaGetLastError());
-    SB_TRY(cudaStreamSynchronize(st->stream));
     st->x_bands = K;
     st->band_cols = band_cols;
     st->a_m = (int)vm; st->a_rowptr = st->v_rowptr; st->a_col = st->v_col; st->a_val = st->v_val;
@@ -469,7 +492,7 @@ static bool build_long_rows_threshold(DeviceState *st)
         }
         int h_ptr[5] = {0, 0, 0, 0, 0};
         if (ok) {
-            coo_band_ptr_kernel<<<1, kThreads, 0, st->stream>>>(m, 4, key_out, d_ptr);  // first sorted row of every bin
+            sorted_key_ptr_kernel<<<1, kThreads, 0, st->stream>>>(m, 4, key_out, d_ptr);  // first sorted row of every bin
             ok = SB_CUDA(cudaGetLastError()) &&
                  SB_CUDA(cudaMemcpyAsync(h_ptr, d_ptr, sizeof(h_ptr), cudaMemcpyDeviceToHost, st->stream)) &&
                  SB_CUDA(cudaStreamSynchronize(st->stream));
@@ -637,24 +660,28 @@ static bool build_csr5(DeviceState *st)
     return alloc_carries(st, p);
 }
 
-// COO column bands (band_coo.cuh): stable bucketing of the CSR entries by col / band_cols
-template <typename T>
-static bool build_band_coo(DeviceState *st)
+// Band segments (band_seg.cuh): stable bucketing of the CSR entries by col / band_cols, segment-end bits, row masks,
+// tile table and the per-block positions of the merge pass.  All temporaries are released on every exit path.
+template <typename T, typename MaskT>
+static bool build_band_seg_t(DeviceState *st)
 {
     const int K = st->coo_bands, nnz = st->nnz, m = st->m;
-    st->x_bands = K;
     st->band_cols = (int)(((long long)st->n + K - 1) / K);
-    int *ent_row = nullptr, *idx_in = nullptr, *idx_out = nullptr, *d_ptr = nullptr;
+    st->seg_mask64 = sizeof(MaskT) == 8;
+    int *ent_row = nullptr, *idx_in = nullptr, *idx_out = nullptr, *d_tab = nullptr, *tile_segs = nullptr, *blk_cnt = nullptr, *blk_scan = nullptr, *d_cross = nullptr;
     unsigned char *key_in = nullptr, *key_out = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
+    int h_ptr[kMaxPieces + 1] = {};
+    auto release = [&]() { dfree(ent_row); dfree(idx_in); dfree(idx_out); dfree(d_tab); dfree(tile_segs); dfree(blk_cnt); dfree(blk_scan); dfree(d_cross);
+                           dfree(key_in); dfree(key_out); dfree(tmp); };
     bool ok = dmalloc(&ent_row, (size_t)nnz) && dmalloc(&idx_in, (size_t)nnz) && dmalloc(&idx_out, (size_t)nnz) &&
-              dmalloc(&key_in, (size_t)nnz) && dmalloc(&key_out, (size_t)nnz) && dmalloc(&d_ptr, (size_t)K + 1) &&
-              dmalloc(&st->coo_row, (size_t)nnz + 8) && dmalloc(&st->coo_col, (size_t)nnz + 8) &&
-              SB_CUDA(cudaMalloc(&st->coo_val, ((size_t)nnz + 8) * sizeof(T)));
+              dmalloc(&key_in, (size_t)nnz) && dmalloc(&key_out, (size_t)nnz) && dmalloc(&d_tab, 4 * (size_t)(K + 1)) &&
+              dmalloc(&d_cross, 1) && SB_CUDA(cudaMalloc(&st->seg_mask, ((size_t)m + 1) * sizeof(MaskT)));
     if (ok) {
-        coo_expand_kernel<<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->band_cols, K, st->rowptr, st->col, ent_row, key_in);
-        coo_iota_kernel<<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_in);
+        bseg_expand_kernel<MaskT><<<blocks_for(m), kThreads, 0, st->stream>>>(m, st->band_cols, K, st->rowptr, st->col, ent_row, key_in,
+                                                                              (MaskT *)st->seg_mask);
+        bseg_iota_kernel<<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_in);
         int bits = 1;
         while ((1 << bits) < K) ++bits;
         ok = SB_CUDA(cudaGetLastError()) &&
@@ -663,35 +690,103 @@ static bool build_band_coo(DeviceState *st)
              SB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, idx_in, idx_out, nnz, 0, bits, st->stream));
     }
     if (ok) {
-        coo_gather_kernel<T><<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_out, ent_row, st->col, (const T *)st->val,
-                                                                          st->coo_row, st->coo_col, (T *)st->coo_val);
-        coo_band_ptr_kernel<<<1, kThreads, 0, st->stream>>>(nnz, K, key_out, d_ptr);
+        sorted_key_ptr_kernel<<<1, kThreads, 0, st->stream>>>(nnz, K, key_out, d_tab);
         ok = SB_CUDA(cudaGetLastError()) &&
-             SB_CUDA(cudaMemcpyAsync(st->coo_ptr, d_ptr, ((size_t)K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st->stream)) &&
+             SB_CUDA(cudaMemcpyAsync(h_ptr, d_tab, ((size_t)K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st->stream)) &&
              SB_CUDA(cudaStreamSynchronize(st->stream));
     }
-    dfree(ent_row); dfree(idx_in); dfree(idx_out); dfree(key_in); dfree(key_out); dfree(d_ptr); dfree(tmp);
+    if (!ok) { release(); return false; }
+    // band b occupies slots [seg_ptr[b], seg_ptr[b] + seg_cnt[b]); starts aligned to 4 entries (16 bytes of ColIdx)
+    long long slot = 0;
+    int tiles = 0;
+    for (int b = 0; b < K; ++b) {
+        st->seg_ptr[b] = (int)slot;
+        st->seg_cnt[b] = h_ptr[b + 1] - h_ptr[b];
+        st->seg_tile0[b] = tiles;
+        tiles += ceil_div(st->seg_cnt[b], kSegTile);
+        slot = (slot + st->seg_cnt[b] + 3) & ~3LL;
+    }
+    st->seg_ptr[K] = (int)slot;
+    st->seg_tile0[K] = tiles;
+    st->coo_tiles = st->tiles = tiles;
+    st->seg_groups = ceil_div(m, 32);
+    const size_t gk = (size_t)K * st->seg_groups;
+    const size_t slots = (size_t)slot + 8;
+    int h_tab[4 * (kMaxPieces + 1)];
+    for (int b = 0; b <= K; ++b) {
+        h_tab[b] = h_ptr[b];
+        h_tab[(K + 1) + b] = st->seg_ptr[b];
+        h_tab[2 * (K + 1) + b] = b < K ? st->seg_cnt[b] : 0;
+        h_tab[3 * (K + 1) + b] = st->seg_tile0[b];
+    }
+    ok = dmalloc(&st->seg_col, slots) && SB_CUDA(cudaMalloc(&st->seg_ent_val, slots * sizeof(T))) &&
+         dmalloc(&st->seg_tile_ent, (size_t)tiles + 1) && dmalloc(&st->seg_tile_seg0, (size_t)tiles * kSegChunks + 4) &&
+         dmalloc(&tile_segs, (size_t)tiles * kSegChunks + 4) && dmalloc(&blk_cnt, gk + 1) && dmalloc(&blk_scan, gk + 1) &&
+         dmalloc(&st->seg_gbase, gk + 1) &&
+         SB_CUDA(cudaMemcpyAsync(d_tab, h_tab, 4 * (size_t)(K + 1) * sizeof(int), cudaMemcpyHostToDevice, st->stream)) &&
+         SB_CUDA(cudaMemsetAsync(st->seg_col, 0, slots * sizeof(int), st->stream)) &&
+         SB_CUDA(cudaMemsetAsync(st->seg_ent_val, 0, slots * sizeof(T), st->stream)) &&
+         SB_CUDA(cudaMemsetAsync(tile_segs, 0, ((size_t)tiles * kSegChunks + 4) * sizeof(int), st->stream)) &&
+         SB_CUDA(cudaMemsetAsync(blk_cnt, 0, (gk + 1) * sizeof(int), st->stream)) &&
+         SB_CUDA(cudaMemsetAsync(d_cross, 0, sizeof(int), st->stream));
+    int h_cross = 0, h_segs[2] = {0, 0};
+    if (ok) {
+        bseg_gather_kernel<T><<<blocks_for(nnz), kThreads, 0, st->stream>>>(nnz, idx_out, key_out, ent_row, st->col, (const T *)st->val, d_tab,
+                                                                           d_tab + (K + 1), st->seg_col, (T *)st->seg_ent_val);
+        bseg_tile_kernel<<<blocks_for((long long)tiles * 32), kThreads, 0, st->stream>>>(tiles, K, st->band_cols, st->n, st->vsize, d_tab + 3 * (K + 1), d_tab + (K + 1), d_tab + 2 * (K + 1),
+                                                                                         st->seg_col, st->seg_tile_ent, tile_segs, d_cross);
+        bseg_group_count_kernel<MaskT><<<blocks_for((long long)st->seg_groups * 32), kThreads, 0, st->stream>>>(m, K, st->seg_groups, (const MaskT *)st->seg_mask, blk_cnt);
+        ok = SB_CUDA(cudaGetLastError()) && exclusive_scan(tile_segs, st->seg_tile_seg0, tiles * kSegChunks + 1, st->stream) &&
+             gk + 1 < 0x7fffffffULL && exclusive_scan(blk_cnt, blk_scan, (int)gk + 1, st->stream);
+        if (ok) {
+            bseg_transpose_kernel<<<blocks_for((long long)gk), kThreads, 0, st->stream>>>(K, st->seg_groups, blk_scan, st->seg_gbase);
+            ok = SB_CUDA(cudaGetLastError());
+        }
+        ok = ok &&
+             SB_CUDA(cudaMemcpy(&h_segs[0], st->seg_tile_seg0 + (size_t)tiles * kSegChunks, sizeof(int), cudaMemcpyDeviceToHost)) &&
+             SB_CUDA(cudaMemcpy(&h_segs[1], blk_scan + gk, sizeof(int), cudaMemcpyDeviceToHost)) &&
+             SB_CUDA(cudaMemcpy(&h_cross, d_cross, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    release();
     if (!ok) return false;
-    st->coo_tiles = 0;
-    for (int b = 0; b < K; ++b) st->coo_tiles += ceil_div((long long)st->coo_ptr[b + 1] - st->coo_ptr[b], kCooTile);
-    st->tiles = st->coo_tiles;
-    if (!alloc_carries(st, st->coo_tiles)) return false;
-    st->kernel = SPMV_B200_KERNEL_BAND_COO;
+    if (h_segs[0] != h_segs[1]) { set_error("band segments: %d segment ends but %d (row, band) pairs", h_segs[0], h_segs[1]); return false; }
+    st->seg_total = h_segs[0];
+    st->seg_cross = h_cross != 0;
+    if (!SB_CUDA(cudaMalloc(&st->seg_sums, ((size_t)st->seg_total + 8) * sizeof(T))) || !dmalloc(&st->seg_ticket, 1)) return false;
+    if (!alloc_carries(st, tiles * kSegChunks)) return false;  // one carry slot per 256-entry chunk
+    st->x_bands = K;
+    st->kernel = SPMV_B200_KERNEL_BAND_SEG;
     return true;
+}
+
+template <typename T>
+static bool build_band_seg(DeviceState *st)
+{
+    return st->coo_bands <= 32 ? build_band_seg_t<T, uint32_t>(st) : build_band_seg_t<T, unsigned long long>(st);
 }
 
 template <typename T>
 static bool build_method(DeviceState *st, spmv_Handle *h, int method)
 {
     if (st->coo_bands > 1 && method != Method_Serial) {
-        if (method == Method_Balanced || method == Method_Balanced2) {
-            // keep what a client reads from the handle: the reference's Balanced <-> Balanced2 rule (a10)
-            st->ref_T = (int)(h->nthreads ? (h->nthreads > (1u << 24) ? (1u << 24) : h->nthreads) : 1);
-            int ref_starved = 0;
-            if (!build_splitter(st, st->m, st->rowptr, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
-            h->spmvMethod = ref_starved ? Method_Balanced2 : Method_Balanced;
+        if (build_band_seg<T>(st)) {
+            if (method == Method_Balanced || method == Method_Balanced2) {
+                // keep what a client reads from the handle: the reference's Balanced <-> Balanced2 rule (a10)
+                st->ref_T = (int)(h->nthreads ? (h->nthreads > (1u << 24) ? (1u << 24) : h->nthreads) : 1);
+                int ref_starved = 0;
+                if (!build_splitter(st, st->m, st->rowptr, st->ref_T, &st->ref_splitter, &ref_starved)) return false;
+                h->spmvMethod = ref_starved ? Method_Balanced2 : Method_Balanced;
+            }
+            return true;
         }
-        return build_band_coo<T>(st);
+        // an optional layout: fall back to the method's own kernel on the plain CSR view
+        cudaGetLastError();
+        free_layouts(st);
+        spmv_b200_clear_error();
+        st->coo_bands = 0;
+        st->x_bands = 1;
+        st->kernel = SPMV_B200_KERNEL_NONE;
+        st->layout_fallbacks++;
     }
     switch (method) {
     case Method_Serial:
@@ -700,8 +795,17 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
     case Method_Parallel:
         st->tpr = pick_tpr(st->nnz, st->a_m);
         st->kernel = SPMV_B200_KERNEL_CSR_VECTOR;
-        if (!build_long_rows_threshold(st)) return false;
-        return build_pipeline(st);
+        if (!build_long_rows_threshold(st)) {  // bins / long-row list are speed-ups: plain CSR-vector still works
+            cudaGetLastError();
+            free_long_rows(st);
+            dfree(st->bin_list); st->bin_list = nullptr;
+            st->binned = false;
+            st->long_thr = 0x7fffffff;
+            spmv_b200_clear_error();
+            st->layout_fallbacks++;
+        }
+        if (!build_pipeline(st)) { cudaGetLastError(); st->pipeline = false; spmv_b200_clear_error(); }
+        return true;
     case Method_Balanced:
     case Method_Balanced2: {
         // mirror of the reference's demotion / promotion rule with the CALLER's nthreads (a10,
@@ -817,7 +921,7 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
     SB_TRY(cudaStreamSynchronize(st->stream));
     // Our own upload of the CSR is dead weight once every kernel of the handle reads a re-laid-out copy (the
     // band-major copy or the COO bands): give those gigabytes back (an adopted device CSR is the caller's).
-    if (st->owns_csr && (st->kernel == SPMV_B200_KERNEL_BAND_COO || st->a_rowptr != st->rowptr)) {
+    if (st->owns_csr && (st->kernel == SPMV_B200_KERNEL_BAND_SEG || st->a_rowptr != st->rowptr)) {
         dfree(st->rowptr); dfree(st->col); dfree(st->val);
         st->rowptr = st->col = nullptr;
         st->val = nullptr;
@@ -877,6 +981,63 @@ csr_tail_kernel(int row0, int m, int long_thr, const int *__restrict__ rowptr, c
     if (lane == 0) y[row] = sum;
 }
 
+static int opt_cached_seg_prefetch()
+{
+    static const int v = (int)opt("seg_prefetch");  // read once: spmv() is the hot path
+    return v;
+}
+
+// band segments, pass 1 over the tiles of bands [b0, b0 + count)
+template <typename T>
+static bool launch_seg_bands(DeviceState *st, int b0, int count, const T *x)
+{
+    const int t0 = st->seg_tile0[b0], t1 = st->seg_tile0[b0 + count];
+    if (t1 <= t0) return true;
+    if (st->seg_grid == 0) {  // persistent CTAs: option seg_ctas per SM (shared memory AND registers allow 2 or 3)
+        st->seg_ctas = (int)opt("seg_ctas");
+        if (st->seg_ctas != 3) st->seg_ctas = 2;
+        const void *fn = st->seg_ctas == 3 ? (const void *)bseg_kernel<T, 3> : (const void *)bseg_kernel<T, 2>;
+        SB_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bseg_smem_bytes<T>()));
+        // leave the rest of the unified array to L1: the gathers need lines for their outstanding misses
+        const int carve = (int)((st->seg_ctas * (bseg_smem_bytes<T>() + 2048) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        SB_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
+        st->seg_grid = st->seg_ctas * (st->dev_sms > 0 ? st->dev_sms : 1);
+    }
+    const int grid = t1 - t0 < st->seg_grid ? t1 - t0 : st->seg_grid;
+    // ticket counter of the dynamic tile schedule: tickets 0 .. 3*grid-1 are implicit (every CTA's first three tiles)
+    set_int_kernel<<<1, 1, 0, st->stream>>>(st->seg_ticket, kSegStages * grid);
+    // L2 prefetch of the next band's x slice pays only when two slices fit the part of L2 random gathers can use
+    // (measured on the C5 shard: 64 MiB slices 5.78 -> 6.13 ms with it, 32 MiB slices 5.81 -> 5.76 ms and DRAM reads
+    // 14.0 -> 9.9 GB); option seg_prefetch: 0 = never, 1 = automatic, 2 = always
+    const int pf_opt = opt_cached_seg_prefetch();
+    const bool two_fit = 2.0 * (double)st->band_cols * st->vsize <= 0.53 * (double)st->dev_l2;
+    const int pf_on = (((uintptr_t)x & 15u) == 0 && (pf_opt == 2 || (pf_opt == 1 && two_fit))) ? 1 : 0;
+#define SB_SEG(MINB) bseg_kernel<T, MINB><<<grid, kSegThreads, bseg_smem_bytes<T>(), st->stream>>>(t0, t1, pf_on, st->seg_ticket, st->seg_tile_ent, st->seg_tile_seg0, \
+        st->seg_col, (const T *)st->seg_ent_val, x, (T *)st->seg_sums, (T *)st->carry_val, st->carry_row)
+    if (st->seg_ctas == 3) SB_SEG(3); else SB_SEG(2);
+#undef SB_SEG
+    count_launch();
+    return SB_CUDA(cudaGetLastError());
+}
+
+// band segments: carries of segments that cross a tile boundary, then pass 2 (y written once, peers included)
+template <typename T>
+static bool launch_seg_finish(DeviceState *st, T *y_out)
+{
+    cudaStream_t s = st->stream;
+    if (st->seg_cross) launch_carry_fixup<T>(st, s, st->tiles * kSegChunks, st->carry_row, (const T *)st->carry_val, (T *)st->seg_sums);
+    PeerList<T> pr;
+    pr.n = st->n_peers;
+    for (int i = 0; i < kMaxPeers; ++i) pr.p[i] = (T *)st->peers[i];
+#define SB_MERGE(M, P) bseg_merge_kernel<T, M, P><<<blocks_for((long long)st->seg_groups * 32), kThreads, 0, s>>>(0, st->m, st->coo_bands, (const M *)st->seg_mask, \
+                                                                                     st->seg_gbase, (const T *)st->seg_sums, y_out, pr)
+    if (st->seg_mask64) { if (pr.n > 0) SB_MERGE(unsigned long long, true); else SB_MERGE(unsigned long long, false); }
+    else { if (pr.n > 0) SB_MERGE(uint32_t, true); else SB_MERGE(uint32_t, false); }
+#undef SB_MERGE
+    count_launch();
+    return SB_CUDA(cudaGetLastError());
+}
+
 template <typename T>
 static bool launch(DeviceState *st, const T *x, T *y_out)
 {
@@ -885,28 +1046,10 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     if (st->kernel == SPMV_B200_KERNEL_NONE) {  // nnz == 0: y = 0
         return SB_CUDA(cudaMemsetAsync(y_out, 0, (size_t)st->m * sizeof(T), s));  // all-zero bits = +0.0
     }
-    if (st->kernel == SPMV_B200_KERNEL_BAND_COO) {
-        // y = 0, then one launch per band (ascending: each adds its segment sums to y), then the carries
-        if (!SB_CUDA(cudaMemsetAsync(y_out, 0, (size_t)st->m * sizeof(T), s))) return false;
-        int tile_base = 0;
-        for (int b = 0; b < st->coo_bands; ++b) {
-            const int e0 = st->coo_ptr[b], e1 = st->coo_ptr[b + 1];
-            const int tiles = ceil_div((long long)e1 - e0, kCooTile);
-            if (tiles <= 0) continue;
-            band_coo_kernel<T><<<tiles, kThreads, 0, s>>>(e0, e1, tile_base, st->coo_row, st->coo_col, (const T *)st->coo_val, x, y_out,
-                                                         (T *)st->carry_val, st->carry_row);
-            launch_carry_fixup<T>(st, s, tiles, st->carry_row + tile_base, (const T *)st->carry_val + tile_base, y_out);
-            tile_base += tiles;
-            count_launch();
-        }
-        if (st->n_peers > 0) {
-            PeerList<T> pr;
-            pr.n = st->n_peers;
-            for (int i = 0; i < kMaxPeers; ++i) pr.p[i] = (T *)st->peers[i];
-            peer_copy_kernel<T><<<blocks_for(st->m), kThreads, 0, s>>>(st->m, y_out, pr);
-            count_launch();
-        }
-        return SB_CUDA(cudaGetLastError());
+    if (st->kernel == SPMV_B200_KERNEL_BAND_SEG) {
+        // pass 1: segment sums of every tile (one launch, tiles in band order); carries of segments that cross a
+        // tile boundary; pass 2: every row adds its segment sums in band order and writes y once
+        return launch_seg_bands<T>(st, 0, st->coo_bands, x) && launch_seg_finish<T>(st, y_out);
     }
     // the active view: the CSR itself, or its band-major copy writing the virtual y
     const int m = st->a_m;
@@ -1188,11 +1331,9 @@ void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASI
     h->RowPtr = RowPtr;  // borrowed, never written (common.c:157-159)
     h->ColIdx = ColIdx;
     h->Matrix_Val = Matrix_Val;
-    if (method == Method_CSR5SPMV && size != sizeof(double)) {
-        // the reference silently runs SELL for fp32 "CSR5" (common.c:177-180); we run a real fp32 CSR5
-        // but keep what a client would read from the handle
-        h->spmvMethod = Method_CSR5SPMV;
-    }
+    // (fp32 Method_CSR5SPMV: the reference silently runs SELL and stores Method_SellCSigma in the handle,
+    // common.c:177-180; here it is a real fp32 CSR5 and the public field keeps Method_CSR5SPMV -- a documented
+    // deviation, include/spmv.h)
     DeviceState *st = new DeviceState();
     h->extraHandle = st;
     st->ok = build_state(st, h, m, n, RowPtr, ColIdx, Matrix_Val, method);
@@ -1223,9 +1364,15 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
     if (!x_dev) {
         if (xb && !SB_CUDA(cudaMemcpyAsync(st->x_stage, Vector_Val_X, xb, cudaMemcpyHostToDevice, st->stream))) return;
         xd = st->x_stage;
+        if (y_dev && xb) {
+            // host x, device y: the call returns without a stream sync, but the caller may reuse X at once (a pinned
+            // X makes this copy truly asynchronous): wait for the copy alone
+            if (!st->ev_x) { if (!SB_CUDA(cudaEventCreateWithFlags(&st->ev_x, cudaEventDisableTiming))) return; }
+            if (!SB_CUDA(cudaEventRecord(st->ev_x, st->stream)) || !SB_CUDA(cudaEventSynchronize(st->ev_x))) return;
+        }
     }
     if (!y_dev) yd = st->y_stage;
-    if (st->x_window && xd != st->window_base && xb && st->kernel != SPMV_B200_KERNEL_BAND_COO) {
+    if (st->x_window && xd != st->window_base && xb && st->kernel != SPMV_B200_KERNEL_BAND_SEG) {
         // optional: mark x as persisting for everything launched on this stream
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
@@ -1289,6 +1436,94 @@ int spmv_b200_set_y_peers(spmv_Handle_t handle, int count, void *const *device_p
     st->n_peers = count;
     for (int i = 0; i < kMaxPeers; ++i) st->peers[i] = i < count ? device_ptrs[i] : nullptr;
     return 0;
+}
+
+// ---- column stages: the contribution of a range of column bands, then the fold ----------------------
+static bool stageable(const DeviceState *st)
+{
+    if (!st || !st->ok || st->x_bands <= 1) return false;
+    if (st->kernel == SPMV_B200_KERNEL_BAND_SEG) return true;
+    return st->kernel == SPMV_B200_KERNEL_CSR_VECTOR && !st->binned && st->lr_rows == 0;
+}
+
+int spmv_b200_bands(spmv_Handle_t handle)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || !st->ok) return -1;
+    return stageable(st) ? st->x_bands : 1;
+}
+
+int spmv_b200_band_columns(spmv_Handle_t handle, int band, long long *col_lo, long long *col_hi)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || !st->ok || band < 0) return -1;
+    const int K = stageable(st) ? st->x_bands : 1;
+    if (band >= K) return -1;
+    const long long lo = K == 1 ? 0 : (long long)band * st->band_cols;
+    long long hi = K == 1 ? st->n : lo + st->band_cols;
+    if (band == K - 1 || hi > st->n) hi = st->n;
+    if (col_lo) *col_lo = lo < st->n ? lo : st->n;
+    if (col_hi) *col_hi = hi;
+    return 0;
+}
+
+int spmv_b200_spmv_bands(spmv_Handle_t handle, int band_first, int band_count, const void *x_device)
+{
+    DeviceState *st = state_of(handle);
+    if (!stageable(st) || band_first < 0 || band_count < 0 || band_first + band_count > st->x_bands) return -1;
+    if (band_count == 0) return 0;
+    if (!is_device_ptr(x_device)) { set_error("spmv_b200_spmv_bands: x must be a device pointer"); return -1; }
+    DeviceGuard guard(st->device);
+    bool ok;
+    if (st->kernel == SPMV_B200_KERNEL_BAND_SEG) {
+        ok = st->vsize == 8 ? launch_seg_bands<double>(st, band_first, band_count, (const double *)x_device)
+                            : launch_seg_bands<float>(st, band_first, band_count, (const float *)x_device);
+    } else {
+        const int r0 = band_first * st->m, r1 = (band_first + band_count) * st->m;  // virtual rows of these bands
+        if (st->vsize == 8) {
+            PeerList<double> none;
+            none.n = 0;
+            for (int i = 0; i < kMaxPeers; ++i) none.p[i] = nullptr;
+            launch_vector_mode<double>(st, r0, r1, (const double *)x_device, (double *)st->v_y, none);
+        } else {
+            PeerList<float> none;
+            none.n = 0;
+            for (int i = 0; i < kMaxPeers; ++i) none.p[i] = nullptr;
+            launch_vector_mode<float>(st, r0, r1, (const float *)x_device, (float *)st->v_y, none);
+        }
+        ok = SB_CUDA(cudaGetLastError());
+    }
+    return ok ? 0 : -1;
+}
+
+}  // extern "C"
+
+template <typename T>
+static bool finish_banded(DeviceState *st, T *y)
+{
+    PeerList<T> peers;
+    peers.n = st->n_peers;
+    for (int i = 0; i < kMaxPeers; ++i) peers.p[i] = (T *)st->peers[i];
+    if (peers.n > 0) band_reduce_kernel<T, true><<<blocks_for(st->m), kThreads, 0, st->stream>>>(0, st->m, st->m, st->x_bands, (const T *)st->v_y, y, peers);
+    else band_reduce_kernel<T, false><<<blocks_for(st->m), kThreads, 0, st->stream>>>(0, st->m, st->m, st->x_bands, (const T *)st->v_y, y, peers);
+    count_launch();
+    return SB_CUDA(cudaGetLastError());
+}
+
+extern "C" {
+
+int spmv_b200_spmv_finish(spmv_Handle_t handle, void *y_device)
+{
+    DeviceState *st = state_of(handle);
+    if (!stageable(st)) return -1;
+    if (!is_device_ptr(y_device)) { set_error("spmv_b200_spmv_finish: y must be a device pointer"); return -1; }
+    DeviceGuard guard(st->device);
+    bool ok;
+    if (st->kernel == SPMV_B200_KERNEL_BAND_SEG)
+        ok = st->vsize == 8 ? launch_seg_finish<double>(st, (double *)y_device) : launch_seg_finish<float>(st, (float *)y_device);
+    else
+        ok = st->vsize == 8 ? finish_banded<double>(st, (double *)y_device) : finish_banded<float>(st, (float *)y_device);
+    return ok ? 0 : -1;
 }
 
 int spmv_b200_ipc_export(const void *device_ptr, void *handle_out_64)
@@ -1357,6 +1592,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "csr5_num_offsets") return st->c5_num_offsets;
     if (k == "csr5_tail_start") return st->c5_tail_start;
     if (k == "pipeline") return st->pipeline;
+    if (k == "values_snapshotted") return 1;
     if (k == "binned") return st->binned;
     if (k == "pinned_host_buffers") return (int)st->pin[0].registered + (int)st->pin[1].registered;
     if (k == "long_rows") return st->lr_rows;
@@ -1365,7 +1601,10 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "device") return st->device;
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
-    if (k == "coo_bands") return st->coo_bands;
+    if (k == "seg_bands") return st->coo_bands;
+    if (k == "segments") return st->seg_total;
+    if (k == "seg_cross") return st->seg_cross;
+    if (k == "layout_fallbacks") return st->layout_fallbacks;
     if (k == "band_cols") return st->band_cols;
     if (k == "far_permille") return (long long)(st->far_fraction * 1000.0);
     if (k == "active_rows") return st->a_m;
@@ -1404,13 +1643,17 @@ long long spmv_b200_structure(spmv_Handle_t handle, const char *name, void *dst,
     else if (k == "csr5_offsets") { src = st->c5_off; bytes = (size_t)st->c5_num_offsets * 4; }
     else if (k == "csr5_col") { src = st->c5_col; bytes = (size_t)st->nnz * 4; }
     else if (k == "csr5_val") { src = st->c5_val; bytes = (size_t)st->nnz * st->vsize; }
-    else if (k == "coo_row") { src = st->coo_row; bytes = st->coo_row ? (size_t)st->nnz * 4 : 0; }
-    else if (k == "coo_col") { src = st->coo_col; bytes = st->coo_col ? (size_t)st->nnz * 4 : 0; }
-    else if (k == "coo_ptr") {
-        if (!dst) return st->coo_bands > 1 ? (long long)(st->coo_bands + 1) * 4 : 0;
-        if (st->coo_bands <= 1 || dst_bytes < (size_t)(st->coo_bands + 1) * 4) return -1;
-        memcpy(dst, st->coo_ptr, (size_t)(st->coo_bands + 1) * 4);
-        return (long long)(st->coo_bands + 1) * 4;
+    else if (k == "seg_col") { src = st->seg_col; bytes = st->seg_col ? (size_t)st->seg_ptr[st->coo_bands] * 4 : 0; }
+    else if (k == "seg_mask") { src = st->seg_mask; bytes = st->seg_mask ? (size_t)st->m * (st->seg_mask64 ? 8 : 4) : 0; }
+    else if (k == "seg_gbase") { src = st->seg_gbase; bytes = st->seg_gbase ? (size_t)st->coo_bands * st->seg_groups * 4 : 0; }
+    else if (k == "seg_chunk_seg0") { src = st->seg_tile_seg0; bytes = st->seg_tile_seg0 ? ((size_t)st->tiles * kSegChunks + 1) * 4 : 0; }
+    else if (k == "seg_ptr" || k == "seg_cnt") {
+        const int *tab = k == "seg_ptr" ? st->seg_ptr : st->seg_cnt;
+        const size_t need = (size_t)(st->coo_bands + (k == "seg_ptr" ? 1 : 0)) * 4;
+        if (!dst) return st->coo_bands > 1 ? (long long)need : 0;
+        if (st->coo_bands <= 1 || dst_bytes < need) return -1;
+        memcpy(dst, tab, need);
+        return (long long)need;
     }
     else if (k == "band_rowptr") { src = st->v_rowptr; bytes = st->v_rowptr ? ((size_t)st->a_m + 1) * 4 : 0; }
     else if (k == "band_col") { src = st->v_col; bytes = st->v_col ? (size_t)st->nnz * 4 : 0; }

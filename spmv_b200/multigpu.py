@@ -175,3 +175,184 @@ class FusedPowerMethod:
         for b in self.buf:
             api.device_free(b)
         self.buf = []
+
+
+# -------------------------------------------------------------------------------------------------------------
+# Pipelined exchange: the all-gather of iteration k hides behind the SpMV of iteration k+1
+# -------------------------------------------------------------------------------------------------------------
+def band_ready_step(col_lo: int, col_hi: int, splitter: Sequence[int], rank: int) -> int:
+    """Exchange step after which x[col_lo, col_hi) is complete on `rank`: slice g of the new x is produced by rank g
+    (rows = columns of a square matrix) and arrives in step j = (g - rank) mod N of the ring schedule (step 0 = the
+    rank's own slice, already in place).  A band is ready once every owner overlapping its columns has arrived."""
+    world = len(splitter) - 1
+    step = 0
+    for g in range(world):
+        lo, hi = int(splitter[g]), int(splitter[g + 1])
+        if hi > lo and lo < col_hi and hi > col_lo:
+            step = max(step, (g - rank) % world)
+    return step
+
+
+class PipelinedPowerMethod:
+    """x <- A x on N ranks with the y -> x exchange OVERLAPPED with the next SpMV.
+
+    The layouts this library builds for matrices whose x does not fit L2 are banded by columns, and band b of the
+    next SpMV only reads x[col_lo_b, col_hi_b) -- the y slices of the few ranks that own those rows.  So instead of
+    "SpMV, then all-gather, then SpMV" the loop is software-pipelined:
+
+      * exchange k runs on a communication stream as N-1 ring steps; in step j every rank sends its fresh y slice
+        to rank (r - j) and receives the slice of rank (r + j): one permutation per step, so no GPU's NVLink ingress
+        is oversubscribed, and slices arrive in a known order;
+      * SpMV k+1 starts with the bands that only need the rank's OWN slice (already in place) and launches every
+        other band as soon as the steps it depends on have completed (stream waits on events; the host never
+        blocks), through spmv_b200_spmv_bands / spmv_b200_spmv_finish -- the fold adds the band partials in band
+        order whatever order they were computed in, so the result is bit-identical to the plain loop.
+
+    Each rank may hold its rows as SEVERAL handles (row sub-blocks): the reference ABI is int32, so a shard with
+    2^31 or more non-zeros has to be presented as more than one matrix.  `parts` = [(handle, row_lo, row_hi)] with
+    rows relative to the rank's first row; handles expose bands() / band_columns() / spmv_bands() / spmv_finish()
+    / spmv() (spmv_b200.api.Handle, or a CPU stand-in in the gloo tests).
+
+    Transport: NCCL point-to-point (torch.distributed.batch_isend_irecv) over NVLink -- plumbing; what makes the
+    overlap possible is the band-staged kernel interface.
+    """
+
+    def __init__(self, parts, splitter: Sequence[int], x0, group=None, overlap: bool = True):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.splitter = [int(v) for v in splitter]
+        assert len(self.splitter) == self.world + 1 and self.splitter[-1] == x0.numel(), "square matrix expected"
+        self.parts = list(parts)
+        self.lo, self.hi = self.splitter[self.rank], self.splitter[self.rank + 1]
+        assert self.parts and self.parts[0][1] == 0 and self.parts[-1][2] == self.hi - self.lo
+        self.x = [x0.clone(), x0.clone()]
+        self.cuda = x0.is_cuda
+        self.overlap = overlap
+        # schedule[j] = [(part index, first band, band count)] to launch once exchange step j has completed
+        self.schedule = [[] for _ in range(self.world)]
+        self.whole = []  # parts that cannot be staged: plain spmv() after the last step
+        for pi, (h, r0, r1) in enumerate(self.parts):
+            K = h.bands()
+            if K <= 1:
+                self.whole.append(pi)
+                continue
+            steps = [band_ready_step(*h.band_columns(b), self.splitter, self.rank) if overlap else self.world - 1
+                     for b in range(K)]
+            b = 0
+            while b < K:  # runs of consecutive bands that become ready in the same step: one launch each
+                e = b
+                while e + 1 < K and steps[e + 1] == steps[b]:
+                    e += 1
+                self.schedule[steps[b]].append((pi, b, e - b + 1))
+                b = e + 1
+        if self.cuda:
+            self.comm_stream = torch.cuda.Stream()
+            self.ev_recv = [[torch.cuda.Event() for _ in range(self.world)] for _ in range(2)]
+            self.ev_y = [torch.cuda.Event() for _ in range(2)]
+        self.pending = None  # parity of the x buffer an exchange is still filling
+
+    # ---- one exchange: N-1 ring steps on the communication stream; returns nothing, completion is in the events ----
+    def _exchange(self, buf, parity):
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return
+        mine = buf[self.lo:self.hi]
+        if self.cuda:
+            self.ev_y[parity].record()
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(self.ev_y[parity])
+                for j in range(1, self.world):
+                    dst, src = (self.rank - j) % self.world, (self.rank + j) % self.world
+                    ops = []
+                    if mine.numel():
+                        ops.append(dist.P2POp(dist.isend, mine, dst, group=self.group))
+                    theirs = buf[self.splitter[src]:self.splitter[src + 1]]
+                    if theirs.numel():
+                        ops.append(dist.P2POp(dist.irecv, theirs, src, group=self.group))
+                    for w in (dist.batch_isend_irecv(ops) if ops else []):
+                        w.wait()  # orders the communication stream after the step; the host does not block
+                    self.ev_recv[parity][j].record(self.comm_stream)
+        else:
+            for j in range(1, self.world):
+                dst, src = (self.rank - j) % self.world, (self.rank + j) % self.world
+                ops = []
+                if mine.numel():
+                    ops.append(dist.P2POp(dist.isend, mine, dst, group=self.group))
+                theirs = buf[self.splitter[src]:self.splitter[src + 1]]
+                if theirs.numel():
+                    ops.append(dist.P2POp(dist.irecv, theirs, src, group=self.group))
+                for w in (dist.batch_isend_irecv(ops) if ops else []):
+                    w.wait()
+
+    def _spmv(self, xc, xn, wait_parity):
+        """One SpMV in band stages; stage j waits for step j of the exchange that is filling xc (if any)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream() if self.cuda else None
+        for j in range(self.world):
+            if j > 0 and wait_parity is not None and self.cuda:
+                cur.wait_event(self.ev_recv[wait_parity][j])
+            for pi, b0, cnt in self.schedule[j]:
+                self.parts[pi][0].spmv_bands(b0, cnt, xc)
+        for pi in self.whole:
+            h, r0, r1 = self.parts[pi]
+            h.spmv(xc, xn[self.lo + r0:self.lo + r1])
+        for pi, (h, r0, r1) in enumerate(self.parts):
+            if pi not in self.whole:
+                h.spmv_finish(xn[self.lo + r0:self.lo + r1])
+
+    def run(self, iters: int, exchange: bool = True):
+        """`iters` iterations; returns (x_final, ms per iteration).  exchange=False times the staged SpMV alone (x is
+        not advanced between ranks: a pure compute measurement)."""
+        torch = self.torch
+        if self.cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+        else:
+            import time
+            t0 = time.perf_counter()
+        cur = 0
+        wait_parity = None
+        for _ in range(iters):
+            xc, xn = self.x[cur], self.x[1 - cur]
+            self._spmv(xc, xn, wait_parity)
+            if exchange:
+                self._exchange(xn, 1 - cur)
+                wait_parity = 1 - cur
+            cur = 1 - cur
+        if self.cuda:
+            if exchange and self.world > 1 and iters > 0:
+                torch.cuda.current_stream().wait_event(self.ev_recv[cur][self.world - 1])  # the last x is complete
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        else:
+            ms = (time.perf_counter() - t0) * 1e3
+        self.cur = cur
+        return self.x[cur], ms / max(iters, 1)
+
+    def exchange_only(self, iters: int):
+        """The exchange alone, back to back (ms per exchange): what the overlap has to hide."""
+        torch = self.torch
+        if self.world == 1:
+            return 0.0
+        if self.cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+        else:
+            import time
+            t0 = time.perf_counter()
+        scratch = self.x[1 - getattr(self, "cur", 0)]
+        for _ in range(iters):
+            self._exchange(scratch, 0)
+            if self.cuda:
+                torch.cuda.current_stream().wait_event(self.ev_recv[0][self.world - 1])
+        if self.cuda:
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / max(iters, 1)
+        return (time.perf_counter() - t0) * 1e3 / max(iters, 1)

@@ -22,7 +22,7 @@ def test_library_loads_and_exports_everything(libpath):
     L = C.CDLL(libpath)
     for name in api.EXPORTED_FUNCTIONS + api.EXPORTED_DATA:
         assert hasattr(L, name), name
-    assert L.spmv_b200_version() == 100
+    assert L.spmv_b200_version() == 200
 
 
 def test_every_header_declaration_is_in_the_export_list():

@@ -303,27 +303,54 @@ def test_pipelined_host_path_same_bits_as_device_path(libpath, port, serial_ref,
     h2.destroy()
 
 
+def expected_band_segments(a, bands):
+    """numpy restatement of the band-segment layout (band_seg.cuh): entries stably bucketed by col // band_cols,
+    band starts aligned to 4 slots, bit 31 of the column index marks the last entry of a (band, row) run."""
+    bc = -(-a.n // bands)
+    rows = np.repeat(np.arange(a.m, dtype=np.int64), np.diff(a.rowptr))
+    band = np.minimum(a.col // bc, bands - 1)
+    order = np.argsort(band, kind="stable")
+    cnt = np.bincount(band, minlength=bands).astype(np.int64)
+    ptr = np.zeros(bands + 1, dtype=np.int64)
+    for b in range(bands):
+        ptr[b + 1] = (ptr[b] + cnt[b] + 3) & ~3
+    col = np.zeros(int(ptr[bands]), dtype=np.uint32)
+    srows, sband = rows[order], band[order]
+    last = np.ones(len(order), dtype=bool)
+    if len(order) > 1:
+        last[:-1] = (srows[1:] != srows[:-1]) | (sband[1:] != sband[:-1])
+    sorted_start = np.concatenate([[0], np.cumsum(cnt)])
+    for b in range(bands):
+        lo, hi = int(sorted_start[b]), int(sorted_start[b + 1])
+        col[int(ptr[b]):int(ptr[b]) + hi - lo] = a.col[order[lo:hi]].astype(np.uint32) | (last[lo:hi].astype(np.uint32) << 31)
+    mask = np.zeros(a.m, dtype=np.uint64)
+    np.bitwise_or.at(mask, rows, np.uint64(1) << band.astype(np.uint64))
+    return bc, ptr.astype(np.int32), cnt.astype(np.int32), col, mask, int(last.sum())
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
-@pytest.mark.parametrize("bands", [2, 7])
-def test_coo_band_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
-    """Hyper-sparse column bands as row-sorted COO lists (band_coo.cuh), forced on small matrices: every
-    method but Method_Serial runs the band_coo kernel; same error bound, reproducible, and the layout is the
-    stable bucketing of the CSR entries by col // band_cols."""
-    for name in ("uni32", "uni5r", "skew", "hub", "lead_trail_empty", "lap48", "one_long_row", "one_row", "tiny_m3", "empties"):
+@pytest.mark.parametrize("bands", [2, 7, 40])
+def test_band_segment_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
+    """Hyper-sparse column bands as band segments (band_seg.cuh), forced on small matrices: every method but
+    Method_Serial runs the two-pass band-segment kernels; same error bound, reproducible, and the layout is the
+    stable bucketing of the CSR entries by col // band_cols with segment-end bits and per-row band masks
+    (40 bands: 64-bit masks)."""
+    for name in ("uni32", "uni5r", "skew", "hub", "lead_trail_empty", "lap48", "one_long_row", "one_row", "tiny_m3", "empties",
+                 "exact2048"):
         a = CASES[name]().astype(dt)
         x = M.make_x(a.n, 5, dt)
         for method in METHODS:
-            api.set_option("coo_bands", bands)
+            api.set_option("seg_bands", bands)
             try:
                 h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method)
             finally:
-                api.set_option("coo_bands", 0)
-            tag = f"coo{bands}/{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
+                api.set_option("seg_bands", 0)
+            tag = f"seg{bands}/{name}/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
             if method == api.Method_Serial:
-                assert h.kernel == "csr_reforder" and h.info("coo_bands") == 0
+                assert h.kernel == "csr_reforder" and h.info("seg_bands") == 0
             else:
-                assert h.kernel == "band_coo" and h.info("coo_bands") == bands and h.info("x_bands") == bands, tag
-                assert h.info("released_csr") == 1, tag
+                assert h.kernel == "band_seg" and h.info("seg_bands") == bands and h.info("x_bands") == bands, tag
+                assert h.info("released_csr") == 1 and h.info("layout_fallbacks") == 0, tag
             y = np.full(a.m, np.nan, dtype=dt)
             h.spmv(x, y)
             assert not np.isnan(y).any(), tag
@@ -332,25 +359,31 @@ def test_coo_band_layout_keeps_parity(libpath, port, serial_ref, dt, bands):
             h.spmv(x, y2)
             assert bits_equal(y, y2), tag
             if method == api.Method_Parallel:
-                bc = h.info("band_cols")
-                assert bc == -(-a.n // bands)
-                ptr = h.structure("coo_ptr", np.int32)
-                assert len(ptr) == bands + 1
-                rows = np.repeat(np.arange(a.m, dtype=np.int32), np.diff(a.rowptr))
-                band = np.minimum(a.col // bc, bands - 1)
-                order = np.argsort(band, kind="stable")
-                assert np.array_equal(ptr, np.searchsorted(band[order], np.arange(bands + 1)).astype(np.int32))
-                assert np.array_equal(h.structure("coo_row", np.int32), rows[order])
-                assert np.array_equal(h.structure("coo_col", np.int32), a.col[order])
+                bc, ptr, cnt, col, mask, nseg = expected_band_segments(a, bands)
+                assert h.info("band_cols") == bc
+                assert np.array_equal(h.structure("seg_ptr", np.int32), ptr), tag
+                assert np.array_equal(h.structure("seg_cnt", np.int32), cnt), tag
+                assert np.array_equal(h.structure("seg_col", np.uint32), col), tag
+                got_mask = h.structure("seg_mask", np.uint64 if bands > 32 else np.uint32).astype(np.uint64)
+                assert np.array_equal(got_mask, mask), tag
+                assert h.info("segments") == nseg, tag
+                # position of every 32-row group's first segment sum in every band's list: [group][band]
+                groups = -(-a.m // 32)
+                bits = ((mask[:, None] >> np.arange(bands, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.int64)
+                padded = np.zeros((groups * 32, bands), dtype=np.int64)
+                padded[:a.m] = bits
+                cnt_bg = padded.reshape(groups, 32, bands).sum(axis=1).T          # [band][group]
+                base_bg = (np.cumsum(cnt_bg.reshape(-1)) - cnt_bg.reshape(-1)).reshape(bands, groups)
+                assert np.array_equal(h.structure("seg_gbase", np.int32).reshape(groups, bands), base_bg.T.astype(np.int32)), tag
             h.destroy()
     # a Balanced / Balanced2 handle still mirrors the reference's demotion rule for clients that read it
     a = CASES["longrow0"]()
-    api.set_option("coo_bands", 2)
+    api.set_option("seg_bands", 2)
     try:
         h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Balanced, nthreads=4)
     finally:
-        api.set_option("coo_bands", 0)
-    assert h.kernel == "band_coo" and h.struct.spmvMethod == api.Method_Balanced2
+        api.set_option("seg_bands", 0)
+    assert h.kernel == "band_seg" and h.struct.spmvMethod == api.Method_Balanced2
     h.destroy()
 
 
@@ -379,21 +412,21 @@ def test_mega_hub_rows_two_level_carries(libpath, port, serial_ref, dt):
 
 
 def test_pin_host_option_page_locks_recurring_buffers(libpath, port, serial_ref):
-    """Option pin_host (off by default): pageable x / y that come back on consecutive calls are page-locked in
-    place after the second sighting, released when the caller switches buffers; results do not change."""
+    """Option pin_host (on by default, 0 = off): pageable x / y that come back on consecutive calls are page-locked
+    in place after the second sighting, released when the caller switches buffers; results do not change."""
     a = M.laplacian2d(400)  # x, y = 1.28 MB each (>= 1 MiB)
     x = M.make_x(a.n, 3, np.float64)
-    h0 = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+    api.set_option("pin_host", 0)
+    try:
+        h0 = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+    finally:
+        api.set_option("pin_host", 1)
     y0 = np.empty(a.m)
     for _ in range(3):
         h0.spmv(x, y0)
-    assert h0.info("pinned_host_buffers") == 0  # default: the caller's pages are never touched
+    assert h0.info("pinned_host_buffers") == 0  # switched off: the caller's pages are never touched
     h0.destroy()
-    api.set_option("pin_host", 1)
-    try:
-        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
-    finally:
-        api.set_option("pin_host", 0)
+    h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
     y = np.full(a.m, np.nan)
     h.spmv(x, y)
     assert h.info("pinned_host_buffers") == 0 and bits_equal(y, y0)
@@ -449,4 +482,67 @@ def test_spmv_is_cuda_graph_capturable(libpath):
             torch.cuda.synchronize()
             assert torch.equal(gb, want), (name, api.METHOD_NAMES[method])
         h.set_stream(0)
+        h.destroy()
+
+
+def test_spmv_on_a_handle_whose_create_failed_leaves_y_untouched(libpath):
+    """The API returns void: a failed create (here: RowPtr[0] != 0) latches an error, and spmv() on that handle is a
+    no-op that must not write a single byte of y -- on the GPU box, with host and with device y."""
+    import torch
+    a = CASES["uni32"]()
+    bad = a.rowptr.copy()
+    bad[0] = 1
+    api.clear_error()
+    h = api.spmv_create_handle_all_in_one(a.m, a.n, bad, a.col, a.val, 1, api.Method_Parallel, 8)
+    assert h and api.lib().spmv_b200_info(h, b"ok") == 0 and api.last_error() != ""
+    x = M.make_x(a.n, 2, np.float64)
+    y = np.full(a.m, 7.25)
+    api.spmv(h, a.m, bad, a.col, a.val, x, y)
+    assert (y == 7.25).all()
+    yd = torch.full((a.m,), 7.25, dtype=torch.float64, device="cuda")
+    xd = torch.as_tensor(x, device="cuda")
+    api.spmv(h, a.m, bad, a.col, a.val, xd, yd)
+    torch.cuda.synchronize()
+    assert bool((yd == 7.25).all())
+    api.spmv_destory_handle(h)
+    api.clear_error()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["fp64", "fp32"])
+def test_band_staged_spmv_is_bit_identical_in_any_band_order(libpath, dt):
+    """spmv_b200_spmv_bands / spmv_b200_spmv_finish (the interface the pipelined multi-GPU loop is built on): bands
+    staged one by one, in scrambled order and in runs, fold to exactly the y of spmv() -- for the band-major copy of
+    Method_Parallel and for band segments; unbanded handles report one band."""
+    import torch
+    for name in ("uni32", "uni16", "hub", "lap48", "empties"):
+        a = CASES[name]().astype(dt)
+        x = torch.as_tensor(M.make_x(a.n, 9, dt), device="cuda")
+        for opt, bands in (("x_bands", 5), ("seg_bands", 6), ("seg_bands", 37)):
+            api.set_option(opt, bands)
+            api.set_option("long_thr", -1)
+            try:
+                h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_Parallel)
+            finally:
+                api.set_option(opt, 0)
+                api.set_option("long_thr", 0)
+            tag = f"{name}/{dt.__name__}/{opt}={bands}[{h.kernel}]"
+            assert h.bands() == bands, tag
+            cols = [h.band_columns(b) for b in range(bands)]
+            assert cols[0][0] == 0 and cols[-1][1] == a.n and all(cols[i][1] == cols[i + 1][0] or cols[i + 1][0] >= a.n for i in range(bands - 1)), tag
+            y = torch.full((a.m,), float("nan"), dtype=x.dtype, device="cuda")
+            h.spmv(x, y)
+            order = list(np.random.default_rng(3).permutation(bands))
+            y2 = torch.full((a.m,), float("nan"), dtype=x.dtype, device="cuda")
+            for b in order:
+                h.spmv_bands(int(b), 1, x)
+            h.spmv_finish(y2)
+            y3 = torch.full((a.m,), float("nan"), dtype=x.dtype, device="cuda")
+            h.spmv_bands(2, bands - 2, x)
+            h.spmv_bands(0, 2, x)
+            h.spmv_finish(y3)
+            torch.cuda.synchronize()
+            assert torch.equal(y, y2) and torch.equal(y, y3), tag
+            h.destroy()
+        h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, api.Method_SellCSigma)
+        assert h.bands() == 1 and h.band_columns(0) == (0, a.n)
         h.destroy()
