@@ -157,6 +157,18 @@ SPMV_B200_API int spmv_b200_band_columns(spmv_Handle_t handle, int band, long lo
 SPMV_B200_API int spmv_b200_spmv_bands(spmv_Handle_t handle, int band_first, int band_count, const void *x_device);
 SPMV_B200_API int spmv_b200_spmv_finish(spmv_Handle_t handle, void *y_device);
 
+/* ---- stream-ordered copies and flags: a copy-engine exchange over NVLink ---------------------------------------------
+ * The y -> x exchange of the iterated loop moves hundreds of megabytes per GPU; done by kernels (NCCL or peer stores)
+ * it competes with the SpMV for SMs, done by the copy engines it does not.  These three calls are all such an exchange
+ * needs next to the IPC mappings above: a device-to-device copy (dst may be a peer mapping) enqueued on a stream, a
+ * 32-bit flag written after everything earlier on the stream (cuStreamWriteValue32; the flag may live in a peer's
+ * memory), and a wait that holds everything later on the stream until a flag is >= value (cuStreamWaitValue32).  The
+ * flags carry iteration numbers: "my slice of x_k has landed in your buffer", "I have finished reading buffer p".
+ * `cuda_stream` is a cudaStream_t passed as void*.  Return 0 or -1 (spmv_b200_last_error()). */
+SPMV_B200_API int spmv_b200_memcpy_async(void *dst, const void *src, size_t bytes, void *cuda_stream);
+SPMV_B200_API int spmv_b200_stream_write32(void *cuda_stream, void *device_ptr, unsigned value);
+SPMV_B200_API int spmv_b200_stream_wait32_geq(void *cuda_stream, void *device_ptr, unsigned value);
+
 /* ---- device memory helpers for C clients (Python clients use torch tensors) ----------------------- */
 SPMV_B200_API void *spmv_b200_malloc(size_t bytes);
 SPMV_B200_API void spmv_b200_free(void *device_ptr);

@@ -38,7 +38,7 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free",
     "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close",
     "spmv_b200_recommend_method", "spmv_b200_bands", "spmv_b200_band_columns", "spmv_b200_spmv_bands",
-    "spmv_b200_spmv_finish"]
+    "spmv_b200_spmv_finish", "spmv_b200_memcpy_async", "spmv_b200_stream_write32", "spmv_b200_stream_wait32_geq"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -111,6 +111,9 @@ def lib() -> C.CDLL:
     L.spmv_b200_band_columns.argtypes = [spmv_Handle_t, i, C.POINTER(ll), C.POINTER(ll)]
     L.spmv_b200_spmv_bands.argtypes = [spmv_Handle_t, i, i, vp]
     L.spmv_b200_spmv_finish.argtypes = [spmv_Handle_t, vp]
+    L.spmv_b200_memcpy_async.argtypes = [vp, vp, C.c_size_t, vp]
+    L.spmv_b200_stream_write32.argtypes = [vp, vp, C.c_uint]
+    L.spmv_b200_stream_wait32_geq.argtypes = [vp, vp, C.c_uint]
     P = C.POINTER(DeviceCSR)
     L.spmv_b200_gen_laplacian2d.argtypes = [i, i, ul, P]
     L.spmv_b200_gen_stencil27.argtypes = [i, i, i, ul, P]
@@ -271,6 +274,22 @@ def device_free(ptr: int) -> None:
 def device_memcpy(dst, src, nbytes: int, kind: int) -> None:
     """kind 0 H2D, 1 D2H, 2 D2D (synchronous)."""
     if lib().spmv_b200_memcpy(_addr(dst), _addr(src), nbytes, kind) != 0:
+        raise RuntimeError(last_error())
+
+
+def memcpy_async(dst, src, nbytes: int, stream: int) -> None:
+    """Device-to-device copy (dst may be a peer mapping) enqueued on a CUDA stream (raw handle)."""
+    if lib().spmv_b200_memcpy_async(_addr(dst), _addr(src), nbytes, stream) != 0:
+        raise RuntimeError(last_error())
+
+
+def stream_write32(stream: int, ptr: int, value: int) -> None:
+    if lib().spmv_b200_stream_write32(stream, ptr, value) != 0:
+        raise RuntimeError(last_error())
+
+
+def stream_wait32_geq(stream: int, ptr: int, value: int) -> None:
+    if lib().spmv_b200_stream_wait32_geq(stream, ptr, value) != 0:
         raise RuntimeError(last_error())
 
 

@@ -1526,6 +1526,44 @@ int spmv_b200_spmv_finish(spmv_Handle_t handle, void *y_device)
     return ok ? 0 : -1;
 }
 
+// ---- stream-ordered building blocks of a copy-engine exchange (multigpu.py: CopyEnginePowerMethod) ----
+int spmv_b200_memcpy_async(void *dst, const void *src, size_t bytes, void *cuda_stream)
+{
+    if (!bytes) return 0;
+    return SB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream)) ? 0 : -1;
+}
+
+typedef int (*StreamValueFn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned, unsigned);
+static StreamValueFn driver_fn(const char *name)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        set_error("driver entry point %s is not available", name);
+        return nullptr;
+    }
+    return (StreamValueFn)fn;
+}
+
+int spmv_b200_stream_write32(void *cuda_stream, void *device_ptr, unsigned value)
+{
+    static StreamValueFn fn = driver_fn("cuStreamWriteValue32");
+    if (!fn || !device_ptr) return -1;
+    const int rc = fn((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)device_ptr, value, 0 /*CU_STREAM_WRITE_VALUE_DEFAULT*/);
+    if (rc != 0) { set_error("cuStreamWriteValue32 failed (%d)", rc); return -1; }
+    return 0;
+}
+
+int spmv_b200_stream_wait32_geq(void *cuda_stream, void *device_ptr, unsigned value)
+{
+    static StreamValueFn fn = driver_fn("cuStreamWaitValue32");
+    if (!fn || !device_ptr) return -1;
+    const int rc = fn((cudaStream_t)cuda_stream, (unsigned long long)(uintptr_t)device_ptr, value, 0 /*CU_STREAM_WAIT_VALUE_GEQ*/);
+    if (rc != 0) { set_error("cuStreamWaitValue32 failed (%d)", rc); return -1; }
+    return 0;
+}
+
 int spmv_b200_ipc_export(const void *device_ptr, void *handle_out_64)
 {
     if (!device_ptr || !handle_out_64) return -1;

@@ -180,16 +180,31 @@ class FusedPowerMethod:
 # -------------------------------------------------------------------------------------------------------------
 # Pipelined exchange: the all-gather of iteration k hides behind the SpMV of iteration k+1
 # -------------------------------------------------------------------------------------------------------------
+def ring_offsets(world: int):
+    """Offsets d_1 .. d_{N-1} of the exchange schedule: in step j every rank r sends its slice to rank (r - d_j) and
+    receives the slice of rank (r + d_j) -- a permutation per step, so no GPU's NVLink ingress is oversubscribed.
+    The order +1, -1, +2, -2, ... brings the NEIGHBOURING slices first: column bands are contiguous column ranges,
+    so the bands around a rank's own slice complete early whichever side they extend to."""
+    out = [0]
+    for k in range(1, world):
+        d = (k + 1) // 2
+        out.append(d if k % 2 == 1 else -d)
+    return [d % world for d in out]
+
+
 def band_ready_step(col_lo: int, col_hi: int, splitter: Sequence[int], rank: int) -> int:
     """Exchange step after which x[col_lo, col_hi) is complete on `rank`: slice g of the new x is produced by rank g
-    (rows = columns of a square matrix) and arrives in step j = (g - rank) mod N of the ring schedule (step 0 = the
-    rank's own slice, already in place).  A band is ready once every owner overlapping its columns has arrived."""
+    (rows = columns of a square matrix) and arrives in the step j with (rank + d_j) mod N == g of ring_offsets
+    (step 0 = the rank's own slice, already in place).  A band is ready once every owner overlapping its columns has
+    arrived."""
     world = len(splitter) - 1
+    offs = ring_offsets(world)
+    step_of = {(rank + d) % world: j for j, d in enumerate(offs)}
     step = 0
     for g in range(world):
         lo, hi = int(splitter[g]), int(splitter[g + 1])
         if hi > lo and lo < col_hi and hi > col_lo:
-            step = max(step, (g - rank) % world)
+            step = max(step, step_of[g])
     return step
 
 
@@ -200,9 +215,10 @@ class PipelinedPowerMethod:
     next SpMV only reads x[col_lo_b, col_hi_b) -- the y slices of the few ranks that own those rows.  So instead of
     "SpMV, then all-gather, then SpMV" the loop is software-pipelined:
 
-      * exchange k runs on a communication stream as N-1 ring steps; in step j every rank sends its fresh y slice
-        to rank (r - j) and receives the slice of rank (r + j): one permutation per step, so no GPU's NVLink ingress
-        is oversubscribed, and slices arrive in a known order;
+      * exchange k runs on a communication stream as N-1 steps; in step j every rank sends its fresh y slice to
+        rank (r - d_j) and receives the slice of rank (r + d_j), d = +1, -1, +2, -2, ... (ring_offsets): one
+        permutation per step, so no GPU's NVLink ingress is oversubscribed, and slices arrive in a known order,
+        nearest neighbours first;
       * SpMV k+1 starts with the bands that only need the rank's OWN slice (already in place) and launches every
         other band as soon as the steps it depends on have completed (stream waits on events; the host never
         blocks), through spmv_b200_spmv_bands / spmv_b200_spmv_finish -- the fold adds the band partials in band
@@ -252,7 +268,7 @@ class PipelinedPowerMethod:
             self.comm_stream = torch.cuda.Stream()
             self.ev_recv = [[torch.cuda.Event() for _ in range(self.world)] for _ in range(2)]
             self.ev_y = [torch.cuda.Event() for _ in range(2)]
-        self.pending = None  # parity of the x buffer an exchange is still filling
+        self.offsets = ring_offsets(self.world)
 
     # ---- one exchange: N-1 ring steps on the communication stream; returns nothing, completion is in the events ----
     def _exchange(self, buf, parity):
@@ -265,7 +281,8 @@ class PipelinedPowerMethod:
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(self.ev_y[parity])
                 for j in range(1, self.world):
-                    dst, src = (self.rank - j) % self.world, (self.rank + j) % self.world
+                    d = self.offsets[j]
+                    dst, src = (self.rank - d) % self.world, (self.rank + d) % self.world
                     ops = []
                     if mine.numel():
                         ops.append(dist.P2POp(dist.isend, mine, dst, group=self.group))
@@ -277,7 +294,8 @@ class PipelinedPowerMethod:
                     self.ev_recv[parity][j].record(self.comm_stream)
         else:
             for j in range(1, self.world):
-                dst, src = (self.rank - j) % self.world, (self.rank + j) % self.world
+                d = self.offsets[j]
+                dst, src = (self.rank - d) % self.world, (self.rank + d) % self.world
                 ops = []
                 if mine.numel():
                     ops.append(dist.P2POp(dist.isend, mine, dst, group=self.group))
@@ -356,3 +374,175 @@ class PipelinedPowerMethod:
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / max(iters, 1)
         return (time.perf_counter() - t0) * 1e3 / max(iters, 1)
+
+
+class CopyEnginePowerMethod:
+    """The pipelined loop of PipelinedPowerMethod with the exchange done by the COPY ENGINES over NVLink peer
+    mappings instead of NCCL kernels: a persistent SpMV kernel owns every SM, so a communication kernel launched
+    next to it waits for SMs (measured on 2 GPUs: NCCL send/recv steps overlapped only partly, and ran at 367 GB/s);
+    DMA copies need none.
+
+    Per iteration k, rank r, after the fold kernel has written its slice of x_{k+1} into its own buffer:
+      communication stream, for every step j (ring_offsets): wait until the destination has finished READING the
+      target buffer two iterations ago (flag free[dst] >= k-1, written by dst into r's memory), copy the slice into
+      the destination's buffer (cudaMemcpyAsync on the CUDA-IPC mapping: a peer DMA), then write the arrival flag
+      arrive[r] = k+1 into the destination's memory (cuStreamWriteValue32: ordered after the copy);
+      compute stream of iteration k+1: before the bands that need owner s, wait for arrive[s] >= k+1
+      (cuStreamWaitValue32 on local memory); after the fold kernel, write free[r] = k+1 into every peer.
+    No collective, no kernel, no host synchronisation inside the loop.  Same arithmetic as the plain loop: bitwise
+    equal results (asserted by bench.py).
+    """
+
+    def __init__(self, parts, splitter: Sequence[int], x0, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.splitter = [int(v) for v in splitter]
+        self.parts = list(parts)
+        self.n, self.item = x0.numel(), x0.element_size()
+        self.lo, self.hi = self.splitter[self.rank], self.splitter[self.rank + 1]
+        self.dtype, self.device = x0.dtype, x0.device
+        W = self.world
+        nbytes = self.n * self.item
+        self.buf = [api.device_malloc(nbytes), api.device_malloc(nbytes)]
+        for b in self.buf:
+            api.device_memcpy(b, x0, nbytes, 2)
+        self.flags = api.device_malloc(2 * W * 4)  # arrive[W], free[W]
+        zero = torch.zeros(2 * W, dtype=torch.int32, device=x0.device)
+        api.device_memcpy(self.flags, zero, 2 * W * 4, 2)
+        torch.cuda.synchronize()
+        mine = [api.ipc_export(self.buf[0]), api.ipc_export(self.buf[1]), api.ipc_export(self.flags)]
+        if W > 1:
+            everyone = [None] * W
+            dist.all_gather_object(everyone, mine, group=group)
+        else:
+            everyone = [mine]
+        self.opened, self.peer_buf, self.peer_flags = [], {}, {}
+        for q in range(W):
+            if q == self.rank:
+                continue
+            ptrs = [api.ipc_open(hd) for hd in everyone[q]]
+            self.opened += ptrs
+            self.peer_buf[q] = ptrs[:2]
+            self.peer_flags[q] = ptrs[2]
+        self.offsets = ring_offsets(W)
+        self.step_of = {(self.rank + d) % W: j for j, d in enumerate(self.offsets)}
+        self.schedule = [[] for _ in range(W)]
+        self.whole = []
+        for pi, (h, r0, r1) in enumerate(self.parts):
+            K = h.bands()
+            if K <= 1:
+                self.whole.append(pi)
+                continue
+            steps = [band_ready_step(*h.band_columns(b), self.splitter, self.rank) for b in range(K)]
+            b = 0
+            while b < K:
+                e = b
+                while e + 1 < K and steps[e + 1] == steps[b]:
+                    e += 1
+                self.schedule[steps[b]].append((pi, b, e - b + 1))
+                b = e + 1
+        self.comm = torch.cuda.Stream()
+        self.ev_y = [torch.cuda.Event() for _ in range(2)]
+        self.it = 0      # iterations completed so far (flags are monotonic across run() calls)
+        self.cur = 0
+        # flag writes into PEER memory: cuStreamWriteValue32 on the IPC mapping where the driver allows it, else a local
+        # write into a scratch word followed by a 4-byte peer copy (both stream-ordered)
+        self.scratch = api.device_malloc(4 * 2 * W)
+        self.direct_flags = True
+        if W > 1:
+            dist.barrier(group=group)  # every rank has mapped every buffer before anyone writes
+            try:
+                q = next(iter(self.peer_flags))
+                api.stream_write32(self.comm.cuda_stream, self.peer_flags[q] + 4 * self.rank, 0)
+                self.comm.synchronize()
+            except RuntimeError:
+                api.clear_error()
+                self.direct_flags = False
+            dist.barrier(group=group)
+
+    def _flag_to_peer(self, stream_h, q, index, value):
+        dst = self.peer_flags[q] + 4 * index
+        if self.direct_flags:
+            api.stream_write32(stream_h, dst, value)
+        else:
+            word = self.scratch + 4 * (index % (2 * self.world))
+            api.stream_write32(stream_h, word, value)
+            api.memcpy_async(dst, word, 4, stream_h)
+
+    def _arrive(self, owner):  # address of arrive[owner] in MY flags
+        return self.flags + 4 * owner
+
+    def run(self, iters: int, exchange: bool = True):
+        torch, W = self.torch, self.world
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if W > 1:
+            self.dist.barrier(group=self.group)
+        cs = torch.cuda.current_stream()
+        cs_h, comm_h = cs.cuda_stream, self.comm.cuda_stream
+        e0.record()
+        for _ in range(iters):
+            k = self.it
+            xc, xn = self.buf[self.cur], self.buf[1 - self.cur]
+            for j in range(W):
+                if j > 0 and exchange and k > 0:
+                    owner = (self.rank + self.offsets[j]) % W
+                    api.stream_wait32_geq(cs_h, self._arrive(owner), k)  # owner's slice of x_k is in xc
+                for pi, b0, cnt in self.schedule[j]:
+                    self.parts[pi][0].spmv_bands(b0, cnt, xc)
+            if self.whole and exchange and k > 0:
+                for j in range(1, W):
+                    api.stream_wait32_geq(cs_h, self._arrive((self.rank + self.offsets[j]) % W), k)
+            for pi in self.whole:
+                h, r0, r1 = self.parts[pi]
+                h.spmv(xc, xn + (self.lo + r0) * self.item)
+            for pi, (h, r0, r1) in enumerate(self.parts):
+                if pi not in self.whole:
+                    h.spmv_finish(xn + (self.lo + r0) * self.item)
+            if exchange and W > 1:
+                # I have finished reading xc (= buffer `cur`) for iteration k: tell everyone (they write into it next)
+                for q in self.peer_flags:
+                    self._flag_to_peer(cs_h, q, W + self.rank, k + 1)
+                self.ev_y[self.cur].record(cs)
+                self.comm.wait_event(self.ev_y[self.cur])
+                nbytes = (self.hi - self.lo) * self.item
+                for j in range(1, W):
+                    dst = (self.rank - self.offsets[j]) % W
+                    # dst must be done with iteration k-1 (the last reader of ITS buffer 1-cur) before I overwrite it
+                    if k > 0:
+                        api.stream_wait32_geq(comm_h, self.flags + 4 * (W + dst), k)
+                    api.memcpy_async(self.peer_buf[dst][1 - self.cur] + self.lo * self.item, xn + self.lo * self.item, nbytes, comm_h)
+                    self._flag_to_peer(comm_h, dst, self.rank, k + 1)
+            self.cur = 1 - self.cur
+            if exchange:
+                self.it += 1
+        if exchange and W > 1 and iters > 0:
+            for j in range(1, W):  # the last x is complete here
+                api.stream_wait32_geq(cs_h, self._arrive((self.rank + self.offsets[j]) % W), self.it)
+        e1.record()
+        torch.cuda.synchronize()
+        self.comm.synchronize()
+        if not exchange and iters % 2 == 1:
+            self.cur = 1 - self.cur  # a compute-only measurement leaves the loop where it was
+        if W > 1:
+            self.dist.barrier(group=self.group)
+        return e0.elapsed_time(e1) / max(iters, 1)
+
+    def result(self):
+        x = self.torch.empty(self.n, dtype=self.dtype, device=self.device)
+        api.device_memcpy(x, self.buf[self.cur], self.n * self.item, 2)
+        return x
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for p in self.opened:
+            api.ipc_close(p)
+        self.opened = []
+        for b in self.buf + [self.flags, self.scratch]:
+            api.device_free(b)
+        self.buf = []

@@ -183,13 +183,15 @@ def test_band_ready_step_covers_exactly_the_owners_of_a_band():
     for rank in range(4):
         for lo, hi in [(0, 50), (90, 110), (240, 260), (0, 400), (399, 400), (100, 250)]:
             j = G.band_ready_step(lo, hi, split, rank)
-            arrived = {(rank + s) % 4 for s in range(j + 1)}
+            offs = G.ring_offsets(4)
+            assert sorted(offs) == [0, 1, 2, 3] and offs[:3] == [0, 1, 3]   # own, +1, -1, then +2
+            arrived = {(rank + offs[s]) % 4 for s in range(j + 1)}
             covered = set()
             for g in arrived:
                 covered |= set(range(max(lo, split[g]), min(hi, split[g + 1])))
             assert covered == set(range(lo, hi)), (rank, lo, hi, j)
             if j > 0:  # and not a step earlier
-                early = {(rank + s) % 4 for s in range(j)}
+                early = {(rank + offs[s]) % 4 for s in range(j)}
                 cov = set()
                 for g in early:
                     cov |= set(range(max(lo, split[g]), min(hi, split[g + 1])))
