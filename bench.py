@@ -71,6 +71,43 @@ def emit(line: dict):
     out.flush()
 
 
+# A hung collective or a lost flag on one rank would otherwise block every rank until the driver's own limit: each
+# multi-GPU leg runs under a deadline.  When it passes, rank 0 prints the line built from what HAS been measured (the
+# plain loop comes first) with a "watchdog" note, and every rank leaves the process.
+PROGRESS = {}
+
+
+class Watchdog:
+    def __init__(self, rank):
+        self.rank, self.deadline, self.what, self.fallback = rank, None, "", None
+        t = threading.Thread(target=self._run, daemon=True)
+        t.start()
+
+    def arm(self, seconds, what, fallback=None):
+        self.what, self.fallback, self.deadline = what, fallback, time.monotonic() + seconds
+
+    def disarm(self):
+        self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            d = self.deadline
+            if d is not None and time.monotonic() > d:
+                log(f"[watchdog] '{self.what}' did not finish in time: giving up on it")
+                try:
+                    if self.rank == 0 and self.fallback is not None:
+                        line = self.fallback()
+                        if line is not None:
+                            line["watchdog"] = f"leg '{self.what}' exceeded its deadline; numbers measured before it are reported"
+                            emit(line)
+                finally:
+                    os._exit(0)
+
+
+WATCHDOG = None
+
+
 # ------------------------------------------------------------------------------------------------
 # workloads
 # ------------------------------------------------------------------------------------------------
@@ -427,12 +464,21 @@ def power_method_record(tag, log2_n, k, seed, iters, args, torch, dist, rank, wo
     rows_per_part = min(mp, (1 << 30) // k)
     parts = []
     t0 = time.perf_counter()
-    for p0 in range(0, mp, rows_per_part):
-        A = api.gen_uniform(rows_per_part, n, k, seed, rank * mp + p0, False, 8)
-        h = A.handle(METHODS["parallel"])
-        if h.info("released_csr") == 0 and h.kernel == "band_seg":
-            pass
-        parts.append((h, p0, p0 + rows_per_part, A))
+    # Column bands aligned with the owners' slices (band g = the rows rank g produces) when that is no coarser than
+    # what L2 needs: then the band of a rank's own slice can start at once and every other band exactly one exchange
+    # step after the previous one.  (C2 at 8 GPUs with the default 3 bands: no band is complete before step 3 of 7.)
+    aligned = args.align_bands and world >= 3 and tag == "C2"
+    if aligned:
+        api.set_option("x_bands", world)
+    try:
+        for p0 in range(0, mp, rows_per_part):
+            A = api.gen_uniform(rows_per_part, n, k, seed, rank * mp + p0, False, 8)
+            h = A.handle(METHODS["parallel"])
+            parts.append((h, p0, p0 + rows_per_part, A))
+    finally:
+        if aligned:
+            api.set_option("x_bands", 0)
+    for h, _, _, A in parts:
         if h.kernel == "band_seg":
             A.destroy()  # band segments keep their own copy of everything: give the generated CSR back
     torch.cuda.synchronize()
@@ -458,6 +504,9 @@ def power_method_record(tag, log2_n, k, seed, iters, args, torch, dist, rank, wo
     x_plain = x_plain.clone()
     del pm
     t_spmv, t_comm = max_over_ranks(torch, dist, [t_spmv, t_comm])
+    PROGRESS[tag] = {"spmv_ms": t_spmv, "allgather_ms": t_comm, "kernel": kernel, "n": n, "k": k, "mp": mp, "iters": iters}
+    if WATCHDOG is not None:
+        WATCHDOG.arm(240, f"{tag}: pipelined loops", FALLBACK.get("fn"))
 
     # (2) the pipelined loop and (3) its SpMV alone / its exchange alone
     pp = G.PipelinedPowerMethod(hparts, split, x0)
@@ -477,27 +526,32 @@ def power_method_record(tag, log2_n, k, seed, iters, args, torch, dist, rank, wo
     ce = None
     if world > 1 and not args.no_ce:
         try:
-            cp = G.CopyEnginePowerMethod(hparts, split, x0)
+            cp = G.CopyEnginePowerMethod(hparts, split, x0, lanes=args.ce_lanes)
             cp.run(warm)
             cp.close()
-            cp = G.CopyEnginePowerMethod(hparts, split, x0)
+            cp = G.CopyEnginePowerMethod(hparts, split, x0, lanes=args.ce_lanes)
             t_ce = cp.run(iters)
             x_ce = cp.result()
             same_ce = bool(torch.equal(x_ce, x_plain))
             t_ce_alone = cp.run(iters, exchange=False)
-            t_ce, t_ce_alone, bad_ce = max_over_ranks(torch, dist, [t_ce, t_ce_alone, 0.0 if same_ce else 1.0])
-            ce = {"iter_ms": t_ce, "spmv_alone_ms": t_ce_alone, "exposed_exchange_ms": max(t_ce - t_ce_alone, 0.0),
-                  "bitwise_equal_to_plain_loop": bad_ce == 0.0, "direct_peer_flags": cp.direct_flags,
+            t_ce_xchg = cp.run(max(3, iters // 3), compute=False)
+            t_ce, t_ce_alone, t_ce_xchg, bad_ce = max_over_ranks(torch, dist, [t_ce, t_ce_alone, t_ce_xchg, 0.0 if same_ce else 1.0])
+            ce = {"iter_ms": t_ce, "spmv_alone_ms": t_ce_alone, "exchange_alone_ms": t_ce_xchg,
+                  "exposed_exchange_ms": max(t_ce - t_ce_alone, 0.0),
+                  "bands_launched_after_step": [sum(c for _, _, c in step) for step in cp.schedule],
+                  "bitwise_equal_to_plain_loop": bad_ce == 0.0, "direct_peer_flags": cp.direct_flags, "lanes": cp.lanes,
                   "transport": "per step one cudaMemcpyAsync of the y slice into the peer's next-x buffer (CUDA-IPC mapping, "
                                "copy engine over NVLink) + cuStreamWriteValue32 arrival flag; the band-staged SpMV waits per "
                                "band with cuStreamWaitValue32; no kernel and no collective in the exchange"}
             cp.close()
             del x_ce
-            log(f"[{tag} x{world}] copy-engine loop {t_ce:.3f} ms (spmv alone {t_ce_alone:.3f}) | bitwise equal {bad_ce == 0.0}")
+            log(f"[{tag} x{world}] copy-engine loop {t_ce:.3f} ms (spmv alone {t_ce_alone:.3f}, exchange alone {t_ce_xchg:.3f}) | bitwise equal {bad_ce == 0.0}")
         except Exception as e:
             log("copy-engine loop unavailable:", repr(e))
             ce = {"error": repr(e)}
     del x_plain
+    if WATCHDOG is not None:
+        WATCHDOG.disarm()
     rec = {"matrix": f"{tag}: uniform-random {n}x{n}, {k} nnz/row, fp64 CSR, rows sharded over {world} GPU(s) by equal nnz",
            "iters": iters, "rows_per_gpu": mp, "handles_per_gpu": len(parts), "kernel": kernel, "column_bands": bands,
            "create_s": create_s,
@@ -516,6 +570,9 @@ def power_method_record(tag, log2_n, k, seed, iters, args, torch, dist, rank, wo
     log(f"[{tag} x{world}] plain {t_spmv:.3f} + {t_comm:.3f} ms | pipelined {t_iter:.3f} ms (spmv alone {t_staged:.3f}, "
         f"exchange alone {t_xchg:.3f}) | bitwise equal {bad == 0.0}")
     return rec, parts, split, x0
+
+
+FALLBACK = {}
 
 
 def free_parts(parts):
@@ -632,9 +689,34 @@ def multi_gpu(args, torch, api, dist, rank, world, local):
     sh = 6 if args.small else 0
     dev = torch.device("cuda", local)
     iters = max(args.steps, 1)
+    global WATCHDOG
+    WATCHDOG = Watchdog(rank)
+
+    def fallback_line():
+        p = PROGRESS.get("C2")
+        if not p:
+            return None
+        t = p["spmv_ms"] + p["allgather_ms"]
+        nn, mpp = p["n"], p["mp"]
+        bmin = mpp * 32 * 12 + (mpp + 1) * 4 + mpp * 8 + nn * 8
+        pk, src = measured_peak()
+        ach = bmin / p["spmv_ms"] / 1e6
+        line = {"metric": "spmv_gflops_fp64_csr", "value": 2.0 * nn * 32 / t / 1e6, "unit": "GFLOP/s", "n_gpus": world,
+                "steps": p["iters"], "warmup": 2, "ms_per_step": t, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C2 uniform-random {nn}x{nn}, 32 nnz/row, fp64 CSR: one power-method iteration x <- A x "
+                                       f"(SpMV + y->x exchange), rows sharded over {world} GPUs by equal nnz",
+                           "method": "Method_Parallel", "kernel": p["kernel"], "loop": "plain"},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "traffic": None,
+                             "kernel": p["kernel"], "peak_source": src, "algorithmic_bytes_per_launch": bmin},
+                "power_method": {"plain_loop": {"spmv_ms_per_iter": p["spmv_ms"], "allgather_ms_per_iter": p["allgather_ms"], "iter_ms": t}},
+                "e2e": None, "gpu_launches": int(api.launch_count()), "c5_progress": PROGRESS.get("C5")}
+        return line
+    FALLBACK["fn"] = fallback_line
     sampler = ClockSampler(local)
     sampler.start()
     l0 = api.launch_count()
+    WATCHDOG.arm(300, "C2: create + plain loop", fallback_line)
     rec, parts, split, x0 = power_method_record("C2", LOG2_ROWS_C2 - sh, 32, M.SEED_C2, iters, args, torch, dist, rank, world)
     launches = api.launch_count() - l0
     clocks = sampler.result()
@@ -658,6 +740,7 @@ def multi_gpu(args, torch, api, dist, rank, world, local):
     # ---- fused variant of round 1 (peer stores from the kernel that writes y): kept as a measured alternative ----
     fused = None
     if len(parts) == 1 and not args.no_fused:
+        WATCHDOG.arm(180, "C2: fused peer-store loop", fallback_line)
         try:
             xs = x0
             fp = G.FusedPowerMethod(h0, split, xs)
@@ -673,6 +756,7 @@ def multi_gpu(args, torch, api, dist, rank, world, local):
             log("fused power method unavailable:", repr(e))
 
     # ---- e2e: host x / y; every rank uploads ITS slice of x, NVLink all-gather, SpMV, its slice of y back ----
+    WATCHDOG.arm(180, "C2: end-to-end leg", fallback_line)
     lo, hi = split[rank], split[rank + 1]
     hx = torch.empty(mp, dtype=torch.float64, pin_memory=True)
     hx.copy_(x0[lo:hi])
@@ -698,9 +782,36 @@ def multi_gpu(args, torch, api, dist, rank, world, local):
     del x0, xd, yd
     torch.cuda.empty_cache()
 
+    # ---- the line so far: what the watchdog prints if the C5 record hangs ----
+    def build_line(c5):
+        return {
+            "metric": "spmv_gflops_fp64_csr", "value": 2.0 * nnz_total / t_iter / 1e6, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": iters, "warmup": 2, "ms_per_step": t_iter, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2 uniform-random {n}x{n}, 32 nnz/row, fp64 CSR: one power-method iteration x <- A x "
+                                   f"(SpMV + y->x exchange), rows sharded over {world} GPUs by equal nnz",
+                       "method": "Method_Parallel", "kernel": rec["kernel"], "m_per_gpu": mp, "n": n, "nnz_per_gpu": mp * 32,
+                       "min_bytes_per_gpu": bmin_gpu,
+                       "l2": "inputs larger than L2 (%.2f GB per GPU and step); no flush" % (bmin_gpu / 1e9),
+                       "timing": "CUDA events around `steps` back-to-back iterations incl. the exchange, max over ranks",
+                       "loop": best_loop, "loops_ms": loops},
+            "gbs_effective": world * achieved, "frac_of_8TBps_nominal": achieved / 8000.0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": rec["kernel"], "peak_source": peak_src, "algorithmic_bytes_per_launch": bmin_gpu,
+                         "note": "per GPU, from the SpMV-alone time of the row shard"},
+            "power_method": rec, "power_method_fused": fused, "c5": c5,
+            "e2e": {"value": 2.0 * nnz_total / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8, "steps": k,
+                    "api": "per rank: its slice of x from pinned host memory, ncclAllGather of x over NVLink, spmv() on device "
+                           "pointers, its slice of y back to pinned host memory (bytes are totals over all ranks)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+    FALLBACK["fn"] = lambda: build_line({"progress": PROGRESS.get("C5"), "note": "the C5 record did not complete"})
+
     # ---- BASELINE.json configs[4]: C5 at this N ----
     c5 = None
     if args.c5:
+        WATCHDOG.arm(420, "C5: create + plain loop", FALLBACK["fn"])
         try:
             c5, parts5, _, _ = power_method_record("C5", LOG2_ROWS_C5 - sh, 16, M.SEED_C5, min(args.power_iters, 50), args, torch, dist,
                                                    rank, world)
@@ -709,28 +820,8 @@ def multi_gpu(args, torch, api, dist, rank, world, local):
             log("C5 record failed:", repr(e))
             c5 = {"error": repr(e)}
 
-    return {
-        "metric": "spmv_gflops_fp64_csr", "value": 2.0 * nnz_total / t_iter / 1e6, "unit": "GFLOP/s", "n_gpus": world,
-        "steps": iters, "warmup": 2, "ms_per_step": t_iter, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2 uniform-random {n}x{n}, 32 nnz/row, fp64 CSR: one power-method iteration x <- A x "
-                               f"(SpMV + y->x exchange), rows sharded over {world} GPUs by equal nnz",
-                   "method": "Method_Parallel", "kernel": rec["kernel"], "m_per_gpu": mp, "n": n, "nnz_per_gpu": mp * 32,
-                   "min_bytes_per_gpu": bmin_gpu,
-                   "l2": "inputs larger than L2 (%.2f GB per GPU and step); no flush" % (bmin_gpu / 1e9),
-                   "timing": "CUDA events around `steps` back-to-back iterations incl. the exchange, max over ranks",
-                   "loop": best_loop, "loops_ms": loops},
-        "gbs_effective": world * achieved, "frac_of_8TBps_nominal": achieved / 8000.0,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": rec["kernel"], "peak_source": peak_src, "algorithmic_bytes_per_launch": bmin_gpu,
-                     "note": "per GPU, from the SpMV-alone time of the row shard"},
-        "power_method": rec, "power_method_fused": fused, "c5": c5,
-        "e2e": {"value": 2.0 * nnz_total / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 8, "steps": k,
-                "api": "per rank: its slice of x from pinned host memory, ncclAllGather of x over NVLink, spmv() on device "
-                       "pointers, its slice of y back to pinned host memory (bytes are totals over all ranks)"},
-        "gpu_launches": int(launches), "clocks": clocks,
-    }
+    WATCHDOG.disarm()
+    return build_line(c5)
 
 
 def main():
@@ -748,6 +839,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--no-ce", action="store_true", help="skip the copy-engine exchange loop")
+    ap.add_argument("--ce-lanes", type=int, default=1, help="streams (copy engines) a slice is spread over in the copy-engine exchange")
+    ap.add_argument("--align-bands", type=int, default=1, help="N >= 3: as many column bands as ranks for the C2 shards")
     ap.add_argument("--small", action="store_true", help="64x smaller matrices (script debugging only; not a bench)")
     args = ap.parse_args()
     claim_stdout()
