@@ -71,6 +71,12 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *                     reference's sample driver, which reuses one X and one Y for every call); released when the
  *                     caller switches buffers and at clear / destroy.  The caller must not free such a buffer while
  *                     the handle lives.  0 = never touch the caller's pages
+ *   "auto"            1 = every create whose Function is not Method_Serial picks the method itself from statistics it
+ *                     gathers on the device (share of non-zeros in very long rows, mean row length, locality of the
+ *                     column indices): Method_CSR5SPMV for power-law matrices, Method_Parallel for short diagonal-
+ *                     local rows and small matrices, Method_SellCSigma otherwise -- the table of measured winners is
+ *                     in DESIGN.md.  handle->spmvMethod then holds the method that runs, spmv_b200_info(h,
+ *                     "auto_method") too.  0 (default) = run what Function says
  *   "pipeline"        1 (default) = spmv() with HOST x and y on a Method_Parallel handle overlaps the PCIe
  *                     copies with the kernels (x in pieces, y in row chunks); 0 = copy, run, copy
  * Returns 0, or -1 for an unknown key. */

@@ -41,6 +41,7 @@ struct DeviceState {
     int m = 0, n = 0, nnz = 0;
     int vsize = 8;                  // 8 = fp64, 4 = fp32
     int requested = 0;              // SPMV_METHODS asked for at create
+    int auto_method = -1;           // option "auto": the SPMV_METHODS value create picked instead (-1: not used)
     int kernel = SPMV_B200_KERNEL_NONE;
     bool ok = false;                // false => spmv() is a no-op
     bool has_empty_rows = false;

@@ -378,6 +378,19 @@ __global__ void band_locality_kernel(int m, double cols_per_row, int halfwidth, 
     if ((threadIdx.x & 31) == 0 && far) atomicAdd(far_count, far);  // integer counter, builder only
 }
 
+// non-zeros that sit in rows longer than `cut` (automatic method selection: the power-law test)
+__global__ void heavy_rows_kernel(int m, int cut, const int *__restrict__ rowptr, unsigned long long *__restrict__ heavy)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (r < m) {
+        const int len = rowptr[r + 1] - rowptr[r];
+        if (len > cut) v = (unsigned long long)len;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(heavy, v);  // integer counter, builder only
+}
+
 __global__ void band_count_kernel(int m, int bands, int band_cols, const int *__restrict__ rowptr,
                                   const int *__restrict__ col, int *__restrict__ counts)
 {

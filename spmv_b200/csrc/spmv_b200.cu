@@ -52,7 +52,7 @@ struct Options {
                                        {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
                                        {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},    {"row_bins", 1},
+                                       {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},  {"auto", 0},    {"row_bins", 1},
                                        {"pin_host", 1}};
     std::map<std::string, bool> user_set;
 };
@@ -841,6 +841,36 @@ static bool build_method(DeviceState *st, spmv_Handle *h, int method)
     }
 }
 
+// "Matrix inspect and choose best method to run" (the empty heading of the reference's README.md:222), inside create:
+// option "auto" = 1 lets every create whose Function is not Method_Serial pick the SPMV_METHODS value whose GPU layout
+// measured fastest on matrices of that shape (profiles/r02a_bench_c2_n1.json, fraction of the measured HBM peak):
+//   * more than a quarter of the non-zeros in rows much longer than the mean (power-law graphs): Method_CSR5SPMV
+//     (C3: CSR5 0.390, Parallel 0.326, merge-path 0.270);
+//   * short rows (mean <= 8) whose gathers are diagonal-local: Method_Parallel (C1: Parallel 0.605, SELL 0.569);
+//   * everything else: Method_SellCSigma (C2: SELL 0.434, Parallel 0.398; C4: SELL 0.981, Parallel 0.883);
+//   * fewer than 8192 rows: Method_Parallel (nothing to amortise a layout build).
+// The statistics are the ones create gathers on the device anyway (far_fraction of the locality probe) plus one pass
+// over RowPtr.  Method_Serial is never overridden: it promises the reference's bits.
+static int auto_pick_method(DeviceState *st)
+{
+    if (st->m < 8192 || st->nnz <= 0) return Method_Parallel;
+    const double mean = (double)st->nnz / st->m;
+    const int cut = (int)(4.0 * mean) + 16;
+    unsigned long long *heavy = nullptr, h_heavy = 0;
+    bool ok = dmalloc(&heavy, 1) && SB_CUDA(cudaMemsetAsync(heavy, 0, sizeof(*heavy), st->stream));
+    if (ok) {
+        heavy_rows_kernel<<<blocks_for(st->m), kThreads, 0, st->stream>>>(st->m, cut, st->rowptr, heavy);
+        ok = SB_CUDA(cudaGetLastError()) &&
+             SB_CUDA(cudaMemcpyAsync(&h_heavy, heavy, sizeof(h_heavy), cudaMemcpyDeviceToHost, st->stream)) &&
+             SB_CUDA(cudaStreamSynchronize(st->stream));
+    }
+    dfree(heavy);
+    if (!ok) { cudaGetLastError(); spmv_b200_clear_error(); return Method_Parallel; }
+    if (4.0 * (double)h_heavy > (double)st->nnz) return Method_CSR5SPMV;
+    if (mean <= 8.0 && st->far_fraction <= 0.25) return Method_Parallel;
+    return Method_SellCSigma;
+}
+
 static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowPtr, int *ColIdx, void *Val,
                         int method)
 {
@@ -915,6 +945,12 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
     if (m == 0 || st->nnz == 0) {  // nothing to lay out: spmv() only has zeros to write
         st->kernel = SPMV_B200_KERNEL_NONE;
         return true;
+    }
+    st->auto_method = -1;
+    if (opt("auto") != 0 && method != Method_Serial) {
+        method = st->auto_method = auto_pick_method(st);
+        if (st->auto_method == Method_SellCSigma || st->auto_method == Method_CSR5SPMV || st->auto_method == Method_Parallel)
+            h->spmvMethod = (SPMV_METHODS)st->auto_method;  // what actually runs, for clients that read the field
     }
     const bool ok = st->vsize == 8 ? build_method<double>(st, h, method) : build_method<float>(st, h, method);
     if (!ok) return false;
@@ -1639,6 +1675,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "device") return st->device;
     if (k == "has_empty_rows") return st->has_empty_rows;
     if (k == "x_bands") return st->x_bands;
+    if (k == "auto_method") return st->auto_method;
     if (k == "seg_bands") return st->coo_bands;
     if (k == "segments") return st->seg_total;
     if (k == "seg_cross") return st->seg_cross;
