@@ -48,16 +48,10 @@ SPMV_B200_API void spmv_b200_sync(spmv_Handle_t handle);
  *                     merged per row in a second pass), for matrices whose bands would hold fewer than 4 non-zeros
  *                     per row (0 = automatic, -1 = never, 2..64 forced); replaces the kernel of every method except
  *                     Method_Serial
- *   "l2_persist"      bytes of L2 set aside for persisting lines at create (0 = leave, -1 = device max)
- *   "l2_fetch"        cudaLimitMaxL2FetchGranularity at create (0 = leave; 32 / 64 / 128)
- *   "x_window"        1 = put an access-policy window (persisting) over x on the handle's stream
  *   "force_merge"     1 = Method_Balanced2 always runs the merge-path kernel (default: only when a row is
  *                     long enough to starve a row block, the reference's own Balanced2 -> Balanced rule)
- *   "vec"             how the CSR kernels read ColIdx / Val: -1 = automatic (default: 4), 4 = predicated batches of
- *                     8 scalar loads per lane through L1, 1 = aligned 128/256-bit chunks, 2 = scalar loads through
- *                     L1 in a plain loop, 0 = scalar loads bypassing L1
  *   "sell_variant"    SELL kernel flavour: -1 = automatic (default: 2 on diagonal-local matrices, else 0),
- *                     0 = 8 columns per step / 40 registers, 1 = 8 / 32, 2 = 4 / 32, 3 = 4 pipelined, 4 = 8 pipelined
+ *                     0 = 8 columns per step / 40 registers, 2 = 4 columns per step / 32 registers (every warp slot filled)
  *   "sell_cap"        widest SELL slice in columns (default 1024); slices that would be mostly padding are
  *                     narrowed by a cost rule and the cut-off row tails go to the long-row path.  0 = the
  *                     reference's widths (every slice as wide as its longest row)
@@ -87,7 +81,9 @@ SPMV_B200_API long long spmv_b200_get_option(const char *key);
  * spmv_b200_info: scalar facts about a handle.  Keys: "kernel" (internal kernel family, see
  * SPMV_B200_KERNEL_*), "requested", "m", "n", "nnz", "tpr", "parts", "tiles", "sigma", "banner",
  * "slices", "padded_nnz", "csr5_p", "csr5_sigma", "csr5_num_offsets", "csr5_tail_start", "device",
- * "has_empty_rows", "x_bands", "band_cols", "active_rows", "owns_csr", "dev_l2_bytes".  Returns -1 for an unknown key / NULL handle.
+ * "has_empty_rows", "x_bands", "seg_bands", "segments", "band_cols", "active_rows", "owns_csr", "released_csr",
+ * "layout_fallbacks", "auto_method", "values_snapshotted", "pipeline", "dev_l2_bytes".  Returns -1 for an unknown key /
+ * NULL handle.
  *
  * spmv_b200_structure: copy a device layout array to HOST memory.  Returns its size in bytes (call
  * with dst = NULL to size it), or -1.  Names: "splitter" (int[parts+1], a9), "ref_splitter"
@@ -95,7 +91,9 @@ SPMV_B200_API long long spmv_b200_get_option(const char *key);
  * (int[2*(tiles+1)]), "sell_perm" (int[banner], a13), "sell_width" (int[slices]), "sell_slice_ptr"
  * (long long[slices+1]), "sell_col" (int[padded]), "sell_val", "csr5_tile_ptr" (unsigned[p+1], a16),
  * "csr5_tile_desc" (unsigned[p*32], a17), "csr5_offset_ptr" (int[p+1]), "csr5_offsets" (int[num]),
- * "csr5_col" (int[nnz], a18), "csr5_val", "band_rowptr" (int[x_bands*m+1]), "band_col" (int[nnz]). */
+ * "csr5_col" (int[nnz], a18), "csr5_val", "band_rowptr" (int[x_bands*m+1]), "band_col" (int[nnz]); band segments:
+ * "seg_ptr" (int[K+1], first slot of every band), "seg_cnt" (int[K]), "seg_col" (unsigned[slots], bit 31 = last entry of
+ * a segment), "seg_mask" (uint32 / uint64 [m]), "seg_gbase" (int[groups*K]), "seg_chunk_seg0" (int[tiles*8+1]). */
 enum {
     SPMV_B200_KERNEL_NONE = 0,
     SPMV_B200_KERNEL_CSR_REFORDER = 1, /* Method_Serial   */

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--profile-only", type=int, default=0, help="run each variant N times without timing (for ncu)")
     ap.add_argument("--flush", action="store_true")
     args = ap.parse_args()
-    A, n, vsize, desc, seed = bench.make_workload(args.workload, 0, 1, args.small)
+    A, n, vsize, desc, seed, _ = bench.make_workload(args.workload, args.small)
     tdt = torch.float64 if vsize == 8 else torch.float32
     x = torch.empty(n, dtype=tdt, device="cuda")
     api.gen_x(x, n, seed, False, vsize)
@@ -53,9 +53,7 @@ def main():
             for k, v in defaults.items():
                 api.set_option(k, v)
         if yref is None:
-            print("# device: L2 %d MiB, persist max %d MiB, window max %d MiB | limits now: persist %d MiB, fetch %d B" % (
-                h.info("dev_l2_bytes") >> 20, h.info("dev_persist_max") >> 20, h.info("dev_window_max") >> 20,
-                h.info("l2_persist_bytes") >> 20, h.info("l2_fetch_bytes")))
+            print("# device: L2 %d MiB" % (h.info("dev_l2_bytes") >> 20))
         if args.profile_only:
             for _ in range(args.profile_only):
                 h.spmv(x, y)

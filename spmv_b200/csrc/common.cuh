@@ -45,13 +45,8 @@ struct DeviceState {
     int kernel = SPMV_B200_KERNEL_NONE;
     bool ok = false;                // false => spmv() is a no-op
     bool has_empty_rows = false;
-    bool aligned = true;            // ColIdx / Val of the active view are 32-byte aligned
-    int rb_mode = 1;                // the same choice for the row-block kernel
-    int load_mode = 1;              // CSR kernels: 1 = aligned 128/256-bit chunk loads, 2 = scalar via L1, 0 = scalar no-L1
     int dev_sms = 0;
-    long long dev_l2 = 0, dev_persist_max = 0, dev_window_max = 0, cur_persist = 0, cur_fetch = 0;
-    bool x_window = false;
-    const void *window_base = nullptr;
+    long long dev_l2 = 0;
     int layout_fallbacks = 0;       // optional layouts (band copy, band segments, row bins) that could not be built
     int n_peers = 0;                // spmv_b200_set_y_peers
     void *peers[kMaxPeers] = {};
@@ -146,8 +141,8 @@ struct DeviceState {
 
 // ------------------------------------------------------------------------------------------------
 // sm_100a memory primitives.
-//  * matrix streams (ColIdx / Val) are read exactly once per SpMV: non-coherent path, no L1
-//    allocation, L2 evict-first -- 256-bit LDG.E.NA.EFL2.256 where alignment allows;
+//  * matrix streams (ColIdx / Val) are read exactly once per SpMV: non-coherent path, L2 evict-first (the tile
+//    kernels also keep them out of L1; band_seg.cuh stages them with bulk copies instead);
 //  * x is the only re-used operand: read-only path with an L2 evict-last policy so the streams do
 //    not push it out of the 126 MB L2.
 // ------------------------------------------------------------------------------------------------
@@ -237,46 +232,6 @@ __device__ __forceinline__ double ldg_cached(const double *p, uint64_t pol)
     double r;
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
     return r;
-}
-
-// ---- 4-element chunk loads (element index multiple of 4; base 32-byte aligned) ----
-// L2 evict-first, but ALLOWED to allocate in L1: neighbouring rows share chunk sectors, and letting the
-// line live in L1 for a few hundred cycles saves the re-fetch from L2 (measured +1-2 % on C1/C2/C4).
-__device__ __forceinline__ void ldg_stream4(const int *p, int (&r)[4], uint64_t pol)
-{
-    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void ldg_stream4(const float *p, float (&r)[4], uint64_t pol)
-{
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void ldg_stream4(const double *p, double (&r)[4], uint64_t)
-{
-    unsigned long long a, b, c, d;  // one 256-bit load, L2 evict-first encoded in the instruction
-    asm volatile("ld.global.nc.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
-
-                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-    r[0] = __longlong_as_double((long long)a);
-    r[1] = __longlong_as_double((long long)b);
-    r[2] = __longlong_as_double((long long)c);
-    r[3] = __longlong_as_double((long long)d);
-}
-// ---- 8-element chunk loads (element index multiple of 8; 256-bit for 4-byte types) ----
-__device__ __forceinline__ void ldg_stream8(const int *p, int (&r)[8])
-{
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p));
-}
-__device__ __forceinline__ void ldg_stream8(const float *p, float (&r)[8])
-{
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
-                 : "l"(p));
 }
 
 // ---- y stores: written once, never re-read by the kernel ----

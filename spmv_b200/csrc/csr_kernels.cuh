@@ -1,6 +1,6 @@
 // csr_kernels.cuh -- kernels that work directly on the CSR arrays:
 //   csr_reforder_kernel   Method_Serial    (bit-identical summation order to the reference)
-//   csr_vector_kernel     Method_Parallel  (sub-warp per row, 128/256-bit streaming loads)
+//   csr_vector_kernel     Method_Parallel  (sub-warp per row, batched scalar stream loads through L1)
 //   row_block_kernel      Method_Balanced  (one warp per nnz-balanced row block of the csrSplitter)
 //   band_*_kernel         band-major ("virtual row") copy that keeps the gathered slice of x in L2
 #pragma once
@@ -69,117 +69,48 @@ csr_reforder_kernel(int m, const int *__restrict__ rowptr, const int *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// One row, cooperatively by `tpr` lanes, in 4-element chunks aligned to 4 elements so that ColIdx is
-// read with one 128-bit and Val with one 128/256-bit streaming load per lane and chunk.  Elements of
-// a chunk that belong to the neighbouring rows are masked out (they sit in sectors this warp fetches
-// anyway).  The last partial chunk of the whole array is read element-wise (no read past nnz).
+// One row, cooperatively by `tpr` lanes, in predicated batches of 8 entries per lane: every stream load of a batch
+// is in flight before the first gather, so a row of up to 8*tpr entries costs three dependent memory round trips
+// (rowptr, col/val, x) however it is aligned -- what a latency-bound (small, L2-cold) matrix needs.  Scalar loads
+// that allocate in L1 (L2 evict-first): the tpr lanes of a row walk it with stride tpr, so one 32-byte sector
+// serves several lanes and is fetched from L2 once.  (Measured and dropped in round 1, fraction of the HBM peak for
+// aligned 4-element chunk loads / a plain scalar loop / this: C1 0.50 / 0.60 / 0.62, C2 0.385 / 0.36 / 0.40,
+// C4 0.69 / 0.74 / 0.89.  The template parameter is kept as the name of the scheme.)
 // ------------------------------------------------------------------------------------------------
-// one aligned 4-element chunk of a row: masked FMAs into acc
-template <typename T>
-__device__ __forceinline__ void chunk_fma(int j, int start, int end, int nnz4, const int *__restrict__ col,
-                                          const T *__restrict__ val, const T *__restrict__ x, uint64_t pl,
-                                          uint64_t pf, T &acc)
-{
-    if (j < nnz4) {
-        int c[4];
-        T v[4];
-        ldg_stream4(col + j, c, pf);
-        ldg_stream4(val + j, v, pf);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int jj = j + k;
-            if (jj >= start && jj < end) acc = fma_t(v[k], ldg_x(x + c[k], pl), acc);
-        }
-    } else {  // last partial chunk of the whole array: element-wise, never read past nnz
-        for (int k = 0; k < 4; ++k) {
-            const int jj = j + k;
-            if (jj >= start && jj < end)
-                acc = fma_t(ldg_stream(val + jj), ldg_x(x + ldg_stream(col + jj), pl), acc);
-        }
-    }
-}
-
-// MODE 1: aligned 4-element chunks (128/256-bit loads).  MODE 0: scalar loads that bypass L1.  MODE 2: scalar
-// loads that allocate in L1 (L2 evict-first): the tpr lanes of a row walk it with stride tpr, so one 32-byte
-// sector serves several consecutive iterations of the same warp and should be fetched from L2 only once.
-// MODE 4 (the default): as MODE 2, in predicated batches of 8 entries per lane.
 template <typename T, int MODE>
 __device__ __forceinline__ T row_partial(int start, int end, int sl, int tpr, int nnz4,
                                          const int *__restrict__ col, const T *__restrict__ val,
                                          const T *__restrict__ x, uint64_t pl, uint64_t pf)
 {
-    // A lane adds at most kBlock consecutive chunks into one FMA chain.  Rows on regular matrices fit one
-    // block and take the plain loop; a lane that walks a very long row alone (small tpr on a skewed
-    // matrix) folds block sums instead of piling ~sqrt(len) ulps into a single chain, which would miss
-    // the 8*eps*sum|a x| bound.  Fixed order either way: bitwise reproducible.
+    static_assert(MODE == 4, "only the batched scheme is instantiated");
+    (void)nnz4;
+    // A lane adds at most kBlock / 2 batches into one FMA chain: a lane that walks a very long row alone (small
+    // tpr on a skewed matrix) folds block sums instead of piling ~sqrt(len) ulps into a single chain, which would
+    // miss the 8*eps*sum|a x| bound.  Fixed order either way: bitwise reproducible.
     constexpr int kBlock = 64;
+    constexpr int B = 8;  // (4 per batch in 32 registers at full occupancy measured slower on every matrix)
     T sum = 0;
-    if (MODE == 1) {
-        const int step = 4 * tpr;
-        const int first = (start & ~3) + 4 * sl;
-        if (end - first <= kBlock * step) {
-#pragma unroll 2
-            for (int j = first; j < end; j += step) chunk_fma<T>(j, start, end, nnz4, col, val, x, pl, pf, sum);
-        } else {
-            for (int j0 = first; j0 < end; j0 += kBlock * step) {
-                const int jend = (end - j0 > kBlock * step) ? j0 + kBlock * step : end;
-                T acc = 0;
-#pragma unroll 2
-                for (int j = j0; j < jend; j += step) chunk_fma<T>(j, start, end, nnz4, col, val, x, pl, pf, acc);
-                sum += acc;
-            }
-        }
-    } else if (MODE == 4) {
-        // predicated batches of 8 entries per lane: every stream load of a batch is in flight before the first
-        // gather, so a row of up to 8*tpr entries costs three dependent memory round trips (rowptr, col/val, x)
-        // however it is aligned -- what a latency-bound (small, L2-cold) matrix needs
-        constexpr int B = 8;  // (4 per batch in 32 registers at full occupancy measured slower on every matrix)
-        int batches = 0;
-        T acc = 0;
-        for (int j = start + sl; j < end; j += B * tpr) {
-            int c[B];
-            T v[B];
+    int batches = 0;
+    T acc = 0;
+    for (int j = start + sl; j < end; j += B * tpr) {
+        int c[B];
+        T v[B];
 #pragma unroll
-            for (int k = 0; k < B; ++k) {
-                const int jj = j + k * tpr;
-                c[k] = jj < end ? ldg_cached(col + jj, pf) : -1;
-            }
+        for (int k = 0; k < B; ++k) {
+            const int jj = j + k * tpr;
+            c[k] = jj < end ? ldg_cached(col + jj, pf) : -1;
+        }
 #pragma unroll
-            for (int k = 0; k < B; ++k) {
-                const int jj = j + k * tpr;
-                v[k] = jj < end ? ldg_cached(val + jj, pf) : (T)0;
-            }
+        for (int k = 0; k < B; ++k) {
+            const int jj = j + k * tpr;
+            v[k] = jj < end ? ldg_cached(val + jj, pf) : (T)0;
+        }
 #pragma unroll
-            for (int k = 0; k < B; ++k)
-                if (c[k] >= 0) acc = fma_t(v[k], ldg_x(x + c[k], pl), acc);
-            if (++batches == kBlock / 2) { sum += acc; acc = 0; batches = 0; }
-        }
-        sum += acc;
-    } else if (MODE == 2) {
-        if (end - start <= 4 * kBlock * tpr) {
-#pragma unroll 4
-            for (int j = start + sl; j < end; j += tpr)
-                sum = fma_t(ldg_cached(val + j, pf), ldg_x(x + ldg_cached(col + j, pf), pl), sum);
-        } else {
-            for (int j0 = start + sl; j0 < end; j0 += 4 * kBlock * tpr) {
-                const int jend = (end - j0 > 4 * kBlock * tpr) ? j0 + 4 * kBlock * tpr : end;
-                T acc = 0;
-#pragma unroll 4
-                for (int j = j0; j < jend; j += tpr)
-                    acc = fma_t(ldg_cached(val + j, pf), ldg_x(x + ldg_cached(col + j, pf), pl), acc);
-                sum += acc;
-            }
-        }
-    } else {
-        for (int j0 = start + sl; j0 < end; j0 += 4 * kBlock * tpr) {
-            const int jend = (end - j0 > 4 * kBlock * tpr) ? j0 + 4 * kBlock * tpr : end;
-            T acc = 0;
-#pragma unroll 4
-            for (int j = j0; j < jend; j += tpr)
-                acc = fma_t(ldg_stream(val + j), ldg_x(x + ldg_stream(col + j), pl), acc);
-            sum += acc;
-        }
+        for (int k = 0; k < B; ++k)
+            if (c[k] >= 0) acc = fma_t(v[k], ldg_x(x + c[k], pl), acc);
+        if (++batches == kBlock / 2) { sum += acc; acc = 0; batches = 0; }
     }
+    sum += acc;
     return sum;
 }
 

@@ -137,8 +137,11 @@ __global__ void sell_fill_kernel(int slices, const int *__restrict__ rowptr, con
 }
 
 // U = columns per step (all 2U coalesced loads of a step are issued before its U gathers), MINB = CTAs per SM
-// the register allocation is held to, PIPE = issue the next step's stream loads before this step's gathers.
-template <typename T, bool PEERS, int U, int MINB, bool PIPE>
+// the register allocation is held to.  Two flavours are instantiated: U = 8 / 6 CTAs (gather-bound matrices:
+// C2 0.43 vs 0.39) and U = 4 / 8 CTAs, every warp slot of the SM filled (HBM-bound ones: C4 0.86 -> 0.98).
+// (Software-pipelined variants -- the next step's stream loads issued before this step's gathers -- measured no
+// better and were dropped.)
+template <typename T, bool PEERS, int U, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__restrict__ full,
             const int *__restrict__ perm, const int *__restrict__ scol, const T *__restrict__ sval,
@@ -161,49 +164,18 @@ sell_kernel(int slices, const long long *__restrict__ slice_ptr, const int *__re
     int groups = 0;
     int j = 0;
     // columns every row of the slice owns: no padding test (the reference's `full` loop)
-    if (PIPE) {
+    for (; j + U <= f; j += U) {
         int cc[U];
         T vv[U];
-        if (U <= f) {
 #pragma unroll
-            for (int k = 0; k < U; ++k) cc[k] = ldg_stream(c + (size_t)k * kSellC, pf);
+        for (int k = 0; k < U; ++k) cc[k] = ldg_stream(c + (size_t)(j + k) * kSellC, pf);
 #pragma unroll
-            for (int k = 0; k < U; ++k) vv[k] = ldg_stream(v + (size_t)k * kSellC, pf);
-        }
-        for (; j + U <= f; j += U) {
-            int nc[U];
-            T nv[U];
-            const bool more = j + 2 * U <= f;
-            if (more) {
+        for (int k = 0; k < U; ++k) vv[k] = ldg_stream(v + (size_t)(j + k) * kSellC, pf);
+        T part = 0;
 #pragma unroll
-                for (int k = 0; k < U; ++k) nc[k] = ldg_stream(c + (size_t)(j + U + k) * kSellC, pf);
-#pragma unroll
-                for (int k = 0; k < U; ++k) nv[k] = ldg_stream(v + (size_t)(j + U + k) * kSellC, pf);
-            }
-            T part = 0;
-#pragma unroll
-            for (int k = 0; k < U; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
-            mid += part;
-            if (++groups == kGroups) { sum += mid; mid = 0; groups = 0; }
-            if (more) {
-#pragma unroll
-                for (int k = 0; k < U; ++k) { cc[k] = nc[k]; vv[k] = nv[k]; }
-            }
-        }
-    } else {
-        for (; j + U <= f; j += U) {
-            int cc[U];
-            T vv[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) cc[k] = ldg_stream(c + (size_t)(j + k) * kSellC, pf);
-#pragma unroll
-            for (int k = 0; k < U; ++k) vv[k] = ldg_stream(v + (size_t)(j + k) * kSellC, pf);
-            T part = 0;
-#pragma unroll
-            for (int k = 0; k < U; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
-            mid += part;
-            if (++groups == kGroups) { sum += mid; mid = 0; groups = 0; }
-        }
+        for (int k = 0; k < U; ++k) part = fma_t(vv[k], ldg_x(x + cc[k], pl), part);
+        mid += part;
+        if (++groups == kGroups) { sum += mid; mid = 0; groups = 0; }
     }
     // remaining columns, padding (ColIdx == -1) masked as in the reference's `~idx ? ... : 0`
     for (; j < w; j += 4) {

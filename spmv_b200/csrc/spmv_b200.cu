@@ -49,8 +49,7 @@ struct Options {
     std::mutex mu;
     std::map<std::string, long long> v{{"sell_sigma", 256}, {"csr5_sigma", 0}, {"block_nnz", 512},
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
-                                       {"l2_persist", 0},   {"l2_fetch", 0},    {"x_window", 0},
-                                       {"force_merge", 0}, {"vec", -1},    {"sell_cap", 1024},
+                                       {"force_merge", 0}, {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
                                        {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},  {"auto", 0},    {"row_bins", 1},
                                        {"pin_host", 1}};
@@ -218,47 +217,16 @@ static void free_state(DeviceState *st)
     delete st;
 }
 
-// Device-wide L2 controls (options l2_persist / l2_fetch), applied when a handle is created:
-//  * l2_persist: bytes of L2 set aside for evict-last ("persisting") lines, -1 = the device maximum.
-//    The evict-last hint on the x gathers only protects lines inside this carve-out.
-//  * l2_fetch: cudaLimitMaxL2FetchGranularity (32/64/128): bytes pulled from DRAM per L2 miss.
+// Device facts the layout decisions need.  (The persisting-L2 carve-out, cudaLimitMaxL2FetchGranularity and an
+// access-policy window over x were options in round 1; none of them moved any measured configuration -- C2 then, the
+// C5 shard in round 2 -- and they are gone.)
 static void apply_device_limits(DeviceState *st)
 {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, st->device) != cudaSuccess) { cudaGetLastError(); return; }
     st->dev_sms = prop.multiProcessorCount;
     st->dev_l2 = prop.l2CacheSize;
-    st->dev_persist_max = prop.persistingL2CacheMaxSize;
-    st->dev_window_max = prop.accessPolicyMaxWindowSize;
-    long long persist = opt("l2_persist");
-    if (persist != 0) {
-        size_t want = persist < 0 ? (size_t)prop.persistingL2CacheMaxSize : (size_t)persist;
-        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
-    }
-    const long long fetch = opt("l2_fetch");
-    if (fetch == 32 || fetch == 64 || fetch == 128)
-        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch) != cudaSuccess) cudaGetLastError();
-    size_t v = 0;
-    if (cudaDeviceGetLimit(&v, cudaLimitPersistingL2CacheSize) == cudaSuccess) st->cur_persist = (long long)v;
-    if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) == cudaSuccess) st->cur_fetch = (long long)v;
-    st->x_window = opt("x_window") != 0;
     st->pin_host = opt("pin_host") != 0;
-}
-
-// How the CSR kernels read ColIdx / Val.  Option "vec": -1 = automatic, 4 = predicated batches of 8 scalar
-// loads per lane through L1 (every stream load of a row in flight before its first gather), 1 = aligned
-// 4-element chunks (128/256-bit loads; needs 32-byte aligned arrays), 2 = scalar loads through L1 in a plain
-// loop, 0 = scalar loads bypassing L1.  Measured (fraction of the HBM peak, Method_Parallel, modes 1 / 2 / 4):
-// C1 0.50 / 0.60 / 0.62, C2 0.385 / 0.36 / 0.40, C3 - / 0.26 / 0.28, C4 0.69 / 0.74 / 0.89 -- mode 4 everywhere.
-static void resolve_load_mode(DeviceState *st)
-{
-    long long mode = opt("vec");
-    const bool forced = mode >= 0 && mode <= 4 && mode != 3;
-    if (!forced) mode = 4;
-    if (mode == 1 && !st->aligned) mode = 2;
-    st->load_mode = (int)mode;
-    st->rb_mode = st->load_mode;  // the row-block kernel reads the streams the same way (C4 0.71 -> 0.77 in mode 4)
 }
 
 static int pick_tpr(long long nnz, int m)
@@ -298,7 +266,6 @@ static bool build_band_major(DeviceState *st)
         dfree(far);
         if (!probed) return false;  // a 8-byte allocation or a trivial kernel failed: the device is unusable
         st->far_fraction = (double)h_far / (double)st->nnz;
-        resolve_load_mode(st);
     }
     if (bands == 0) {
         bands = 1;
@@ -359,8 +326,6 @@ static bool build_band_major(DeviceState *st)
     st->x_bands = K;
     st->band_cols = band_cols;
     st->a_m = (int)vm; st->a_rowptr = st->v_rowptr; st->a_col = st->v_col; st->a_val = st->v_val;
-    st->aligned = true;  // the band copy is our own 256-byte aligned allocation
-    resolve_load_mode(st);
     return true;
 }
 
@@ -564,7 +529,7 @@ static bool build_sell(DeviceState *st)
     // HBM-bound (diagonal-local) matrices want every warp slot filled: 4 columns per step in 32 registers
     // (C4: 0.86 -> 0.98 of the measured peak); gather-bound ones run best with 8 columns per step (C2: 0.43 vs 0.39)
     st->sell_variant = (int)opt("sell_variant");
-    if (st->sell_variant < 0 || st->sell_variant > 4) st->sell_variant = (st->far_fraction > 0.25) ? 0 : 2;
+    if (st->sell_variant != 0 && st->sell_variant != 2) st->sell_variant = (st->far_fraction > 0.25) ? 0 : 2;
     // covered[r]: entries of row r stored in its slice (sell_width_kernel); tail rows [banner, m) stay CSR,
     // except hub rows, which csr_tail_kernel zeroes and the long-row path then adds as a whole
     long long cap_opt = opt("sell_cap");  // 0 = off (the reference's widths), else the widest slice allowed
@@ -912,7 +877,7 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
         st->val = Val;
         st->owns_csr = false;
     } else {
-        // upload once; 32 bytes of slack so that aligned chunk loads never leave the allocation
+        // upload once (32 bytes of slack behind every array)
         st->owns_csr = true;
         if (!dmalloc(&st->rowptr, (size_t)m + 1 + 8) || !dmalloc(&st->col, (size_t)st->nnz + 8)) return false;
         if (!SB_CUDA(cudaMalloc(&st->val, ((size_t)st->nnz + 8) * st->vsize))) return false;
@@ -923,8 +888,6 @@ static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowP
             SB_TRY(cudaMemcpy(st->val, Val, (size_t)st->nnz * st->vsize, cudaMemcpyHostToDevice));
         }
     }
-    st->aligned = (((uintptr_t)st->col | (uintptr_t)st->val) & 31u) == 0;
-    resolve_load_mode(st);
 
     st->a_m = st->m; st->a_rowptr = st->rowptr; st->a_col = st->col; st->a_val = st->val;
     if (method != Method_Serial) {  // Method_Serial keeps the reference's exact summation order: never banded
@@ -991,10 +954,7 @@ static void launch_vector(DeviceState *st, int tpr, int row0, int row1, const T 
 template <typename T>
 static void launch_vector_mode(DeviceState *st, int row0, int row1, const T *x, T *y, const PeerList<T> &peers, int fuse_bands = 0)
 {
-    if (st->load_mode == 1) launch_vector<T, 1>(st, st->tpr, row0, row1, x, y, peers, fuse_bands);
-    else if (st->load_mode == 4) launch_vector<T, 4>(st, st->tpr, row0, row1, x, y, peers, fuse_bands);
-    else if (st->load_mode == 2) launch_vector<T, 2>(st, st->tpr, row0, row1, x, y, peers, fuse_bands);
-    else launch_vector<T, 0>(st, st->tpr, row0, row1, x, y, peers, fuse_bands);
+    launch_vector<T, 4>(st, st->tpr, row0, row1, x, y, peers, fuse_bands);
 }
 
 // CSR-vector over rows [row0, m) only (the CSR tail of SELL)
@@ -1131,10 +1091,7 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
     case SPMV_B200_KERNEL_ROW_BLOCKS: {
         const int grid = blocks_for((long long)st->parts * 32);
 #define SB_RB(V, P) row_block_kernel<T, V, P><<<grid, kThreads, 0, s>>>(st->parts, st->nnz, st->splitter, st->a_rowptr, st->a_col, val, x, y, direct)
-        if (st->rb_mode == 1) { if (direct.n > 0) SB_RB(1, true); else SB_RB(1, false); }
-        else if (st->rb_mode == 2) { if (direct.n > 0) SB_RB(2, true); else SB_RB(2, false); }
-        else if (st->rb_mode == 4) { if (direct.n > 0) SB_RB(4, true); else SB_RB(4, false); }
-        else { if (direct.n > 0) SB_RB(0, true); else SB_RB(0, false); }
+        if (direct.n > 0) SB_RB(4, true); else SB_RB(4, false);
 #undef SB_RB
         scattered = scattered || !banded;
         count_launch();
@@ -1162,14 +1119,11 @@ static bool launch(DeviceState *st, const T *x, T *y_out)
         if (st->slices > 0) {
             const PeerList<T> &sp = (st->banner == m) ? direct : none;
             const int sgrid = blocks_for((long long)st->slices * 32);
-#define SB_SELL(P, U, MINB, PIPE) sell_kernel<T, P, U, MINB, PIPE><<<sgrid, kThreads, 0, s>>>( \
+#define SB_SELL(P, U, MINB) sell_kernel<T, P, U, MINB><<<sgrid, kThreads, 0, s>>>( \
                 st->slices, st->sell_slice_ptr, st->sell_full, st->sell_perm, st->sell_col, (const T *)st->sell_val, x, y, sp)
-            if (sp.n > 0) SB_SELL(true, 8, 6, false);
-            else if (st->sell_variant == 1) SB_SELL(false, 8, 8, false);
-            else if (st->sell_variant == 2) SB_SELL(false, 4, 8, false);
-            else if (st->sell_variant == 3) SB_SELL(false, 4, 6, true);
-            else if (st->sell_variant == 4) SB_SELL(false, 8, 4, true);
-            else SB_SELL(false, 8, 6, false);
+            if (sp.n > 0) SB_SELL(true, 8, 6);
+            else if (st->sell_variant == 2) SB_SELL(false, 4, 8);
+            else SB_SELL(false, 8, 6);
 #undef SB_SELL
             scattered = scattered || (!banded && st->banner == m);
             count_launch();
@@ -1408,19 +1362,6 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
         }
     }
     if (!y_dev) yd = st->y_stage;
-    if (st->x_window && xd != st->window_base && xb && st->kernel != SPMV_B200_KERNEL_BAND_SEG) {
-        // optional: mark x as persisting for everything launched on this stream
-        cudaStreamAttrValue attr;
-        memset(&attr, 0, sizeof(attr));
-        attr.accessPolicyWindow.base_ptr = const_cast<void *>(xd);
-        attr.accessPolicyWindow.num_bytes = xb < (size_t)st->dev_window_max ? xb : (size_t)st->dev_window_max;
-        const double room = st->cur_persist > 0 ? (double)st->cur_persist / (double)attr.accessPolicyWindow.num_bytes : 0.0;
-        attr.accessPolicyWindow.hitRatio = room >= 1.0 ? 1.0f : (float)room;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        if (cudaStreamSetAttribute(st->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-        st->window_base = xd;
-    }
     const bool ok = st->vsize == 8 ? launch<double>(st, (const double *)xd, (double *)yd)
                                    : launch<float>(st, (const float *)xd, (float *)yd);
     if (!ok) return;
@@ -1685,13 +1626,7 @@ long long spmv_b200_info(spmv_Handle_t handle, const char *key)
     if (k == "active_rows") return st->a_m;
     if (k == "owns_csr") return st->owns_csr;
     if (k == "released_csr") return st->released_csr;
-    if (k == "vec_ok") return st->load_mode == 1;
-    if (k == "load_mode") return st->load_mode;
     if (k == "dev_l2_bytes") return st->dev_l2;
-    if (k == "dev_persist_max") return st->dev_persist_max;
-    if (k == "dev_window_max") return st->dev_window_max;
-    if (k == "l2_persist_bytes") return st->cur_persist;
-    if (k == "l2_fetch_bytes") return st->cur_fetch;
     return -1;
 }
 
