@@ -1,4 +1,6 @@
-"""8-GPU probe of the copy-engine exchange on C5: exchange alone and the full loop for several numbers of lanes."""
+"""8-GPU probe of the copy-engine exchange (C5 or C2 shards): the full loop, the SpMV alone and the exchange alone for
+several numbers of lanes.  Run it under `timeout` (e.g. `timeout 300 python -m torch.distributed.run ... ce_probe.py 1,2 c5`):
+a rank that hangs holds the whole box until gpurun's own limit."""
 import os, sys, time, json
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
