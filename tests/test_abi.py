@@ -118,3 +118,35 @@ def test_no_device_is_a_loud_error_not_a_fallback(libpath):
     assert (y == 123.0).all()
     api.spmv_destory_handle(h)
     api.spmv(None, A.m, A.rowptr, A.col, A.val, np.ones(A.n), y)  # NULL handle: silent no-op (common.c:285)
+
+
+def test_extension_header_is_plain_c_and_the_new_entry_points_are_null_safe(libpath, tmp_path):
+    """include/spmv_b200.h compiles as pedantic C11 (a C client of the reference is C), links against the library,
+    and the round-2 entry points (band-staged SpMV, copy-engine exchange primitives) refuse NULL arguments instead
+    of crashing -- with or without a GPU."""
+    prog = r'''
+#include <stdio.h>
+#include "spmv_b200.h"
+int main(void) {
+    long long lo = -1, hi = -1;
+    spmv_Handle_t h = NULL;
+    int r = 0;
+    r |= (spmv_b200_bands(h) != -1) << 0;
+    r |= (spmv_b200_band_columns(h, 0, &lo, &hi) != -1) << 1;
+    r |= (spmv_b200_spmv_bands(h, 0, 1, NULL) != -1) << 2;
+    r |= (spmv_b200_spmv_finish(h, NULL) != -1) << 3;
+    r |= (spmv_b200_memcpy_async(NULL, NULL, 0, NULL) != 0) << 4;
+    r |= (spmv_b200_stream_write32(NULL, NULL, 1u) != -1) << 5;
+    r |= (spmv_b200_stream_wait32_geq(NULL, NULL, 1u) != -1) << 6;
+    r |= (spmv_b200_set_y_peers(h, 0, NULL) != -1) << 7;
+    printf("%d %d\n", spmv_b200_version(), r);
+    return 0;
+}'''
+    src = tmp_path / "ext.c"
+    src.write_text(prog)
+    exe = tmp_path / "ext"
+    libdir = os.path.dirname(libpath)
+    subprocess.run([GCC, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{INC}", str(src), f"-L{libdir}", "-lspmv_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["200", "0"], out
