@@ -118,6 +118,22 @@ SPMV_B200_API long long spmv_b200_structure(spmv_Handle_t handle, const char *na
  * Method_SellCSigma.  Returns -1 on invalid arguments. */
 SPMV_B200_API int spmv_b200_recommend_method(int m, const int *RowPtr);
 
+/* ---- locality reordering at create (the reference's compiled-out level-3 hook, common.c:144-156) ----------------------
+ * Option "reorder" = 1 (SPMV_B200_REORDER=1): for a square matrix with more than 8096 rows and 100000 non-zeros given
+ * as HOST arrays (the reference's own condition, common.c:145), create computes a symmetric permutation, builds the
+ * device layout of A' = P A P^T, stores the permutation in handle->index (malloc'ed, m+1 ints, index[i] = original row at
+ * position i; freed by clear / destroy) and sets handle->Level_3_opt_used.  The caller then follows the reference's
+ * protocol (src/samples/test_spmv.c:95-101,130-137): x'[i] = x[index[i]] goes in, y[index[i]] = y'[i] comes out.
+ * The two host functions below are what create uses; pure host code, usable without a GPU:
+ *   spmv_b200_reorder      reverse Cuthill-McKee over the row adjacency (components entered at their lowest-degree
+ *                          vertex); index_out[m];
+ *   spmv_b200_permute_csr  A' = P A P^T for a square CSR: row i of A' is row index[i] of A with column c renamed to the
+ *                          position of c, columns ascending inside a row (duplicates keep their order).
+ * Return 0, or -1 (bad arguments, index not a permutation, column outside [0, m)). */
+SPMV_B200_API int spmv_b200_reorder(int m, const int *RowPtr, const int *ColIdx, int *index_out);
+SPMV_B200_API int spmv_b200_permute_csr(int m, const int *RowPtr, const int *ColIdx, const void *Val, unsigned long size,
+                                        const int *index, int *RowPtr_out, int *ColIdx_out, void *Val_out);
+
 /* kernels launched by this process on the spmv() path since load (for benchmark accounting) */
 SPMV_B200_API unsigned long long spmv_b200_launch_count(void);
 

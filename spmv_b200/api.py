@@ -38,7 +38,8 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_gen_uniform", "spmv_b200_gen_rmat", "spmv_b200_gen_x", "spmv_b200_csr_free",
     "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close",
     "spmv_b200_recommend_method", "spmv_b200_bands", "spmv_b200_band_columns", "spmv_b200_spmv_bands",
-    "spmv_b200_spmv_finish", "spmv_b200_memcpy_async", "spmv_b200_stream_write32", "spmv_b200_stream_wait32_geq"]
+    "spmv_b200_spmv_finish", "spmv_b200_memcpy_async", "spmv_b200_stream_write32", "spmv_b200_stream_wait32_geq",
+    "spmv_b200_reorder", "spmv_b200_permute_csr"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -111,6 +112,8 @@ def lib() -> C.CDLL:
     L.spmv_b200_band_columns.argtypes = [spmv_Handle_t, i, C.POINTER(ll), C.POINTER(ll)]
     L.spmv_b200_spmv_bands.argtypes = [spmv_Handle_t, i, i, vp]
     L.spmv_b200_spmv_finish.argtypes = [spmv_Handle_t, vp]
+    L.spmv_b200_reorder.argtypes = [i, vp, vp, vp]
+    L.spmv_b200_permute_csr.argtypes = [i, vp, vp, vp, ul, vp, vp, vp, vp]
     L.spmv_b200_memcpy_async.argtypes = [vp, vp, C.c_size_t, vp]
     L.spmv_b200_stream_write32.argtypes = [vp, vp, C.c_uint]
     L.spmv_b200_stream_wait32_geq.argtypes = [vp, vp, C.c_uint]
@@ -331,6 +334,30 @@ def partition_rows(rowptr: np.ndarray, parts: int) -> np.ndarray:
     if lib().spmv_b200_partition_rows(rp.ctypes.data, len(rp) - 1, parts, out.ctypes.data) != 0:
         raise ValueError("bad partition arguments")
     return out
+
+
+def reorder(rowptr: np.ndarray, col: np.ndarray) -> np.ndarray:
+    """index[i] = original row placed at position i: the permutation create stores in handle->index with option
+    "reorder" (reverse Cuthill-McKee; host code)."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col, dtype=np.int32)
+    out = np.empty(len(rp) - 1, dtype=np.int32)
+    if lib().spmv_b200_reorder(len(rp) - 1, rp.ctypes.data, ci.ctypes.data, out.ctypes.data) != 0:
+        raise ValueError("bad reorder arguments")
+    return out
+
+
+def permute_csr(rowptr, col, val, index):
+    """(rowptr', col', val') of A' = P A P^T (host code)."""
+    rp = np.ascontiguousarray(rowptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col, dtype=np.int32)
+    va = np.ascontiguousarray(val)
+    ix = np.ascontiguousarray(index, dtype=np.int32)
+    rp2, ci2, va2 = np.empty_like(rp), np.empty_like(ci), np.empty_like(va)
+    if lib().spmv_b200_permute_csr(len(rp) - 1, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, va.dtype.itemsize,
+                                   ix.ctypes.data, rp2.ctypes.data, ci2.ctypes.data, va2.ctypes.data) != 0:
+        raise ValueError("bad permute arguments (index must be a permutation, the pattern square)")
+    return rp2, ci2, va2
 
 
 def recommend_method(rowptr: np.ndarray) -> int:

@@ -8,6 +8,7 @@
 #include <string>
 #include <map>
 #include <cmath>
+#include <vector>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -51,7 +52,7 @@ struct Options {
                                        {"tile_items", 8},   {"tpr", 0},         {"x_bands", 0},
                                        {"force_merge", 0}, {"sell_cap", 1024},
                                        {"long_thr", 0},    {"pipeline", 1},   {"sell_variant", -1},
-                                       {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},  {"auto", 0},    {"row_bins", 1},
+                                       {"seg_bands", 0},    {"seg_prefetch", 1}, {"seg_ctas", 2},  {"auto", 0},     {"reorder", 0},    {"row_bins", 1},
                                        {"pin_host", 1}};
     std::map<std::string, bool> user_set;
 };
@@ -1326,6 +1327,31 @@ void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASI
     // deviation, include/spmv.h)
     DeviceState *st = new DeviceState();
     h->extraHandle = st;
+    // Option "reorder": the reference's level-3 hook (common.c:144-156, compiled out upstream).  Same condition as
+    // there (square, > 8096 rows, > 100000 non-zeros), HOST arrays only; the device layout is then built from
+    // A' = P A P^T and the permutation is handed to the caller in handle->index (reorder.cu).
+    std::vector<int> p_rowptr, p_col;
+    std::vector<double> p_val;  // (storage only: 8-byte aligned, holds fp32 or fp64 values)
+    if (opt("reorder") != 0 && m == n && m > 8096 && RowPtr && ColIdx && Matrix_Val && !is_device_ptr(RowPtr) &&
+        RowPtr[0] == 0 && RowPtr[m] > 100000) {
+        const size_t nnz = (size_t)RowPtr[m];
+        int *index = (int *)malloc(((size_t)m + 1) * sizeof(int));
+        bool done = false;
+        if (index && spmv_b200_reorder(m, RowPtr, ColIdx, index) == 0) {
+            p_rowptr.resize((size_t)m + 1);
+            p_col.resize(nnz);
+            p_val.resize(nnz);
+            done = spmv_b200_permute_csr(m, RowPtr, ColIdx, Matrix_Val, size, index, p_rowptr.data(), p_col.data(), p_val.data()) == 0;
+        }
+        if (done) {
+            index[m] = m;
+            h->index = index;           // freed by spmv_clear_handle
+            h->Level_3_opt_used = 1;
+            st->ok = build_state(st, h, m, n, p_rowptr.data(), p_col.data(), p_val.data(), method);
+            return;
+        }
+        free(index);
+    }
     st->ok = build_state(st, h, m, n, RowPtr, ColIdx, Matrix_Val, method);
 }
 
@@ -1375,6 +1401,7 @@ void spmv_clear_handle(spmv_Handle_t this_handle)  // reference gemv_Handle_clea
 {
     if (!this_handle) return;
     free_state(state_of(this_handle));
+    if (this_handle->Level_3_opt_used && this_handle->index) free(this_handle->index);  // ours (option "reorder")
     handle_init(this_handle);
 }
 

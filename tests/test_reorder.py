@@ -1,0 +1,81 @@
+"""SURVEY.md 8(f)-4, the host half: the permutation create stores in handle->index with option "reorder" (reverse
+Cuthill-McKee) and the permuted matrix A' = P A P^T, checked on the CPU: valid permutation, bandwidth actually
+shrinks on a scrambled mesh, A' is exactly the permuted operator, and the reference's calling protocol
+(x'[i] = x[index[i]], y[index[i]] = y'[i]; src/samples/test_spmv.c:95-101,130-137) reproduces y = A x."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from spmv_b200 import api, matrices as M
+
+
+def _scramble(A, seed):
+    """B = Q A Q^T for a random permutation Q (a mesh whose numbering has been destroyed)."""
+    rng = np.random.default_rng(seed)
+    q = rng.permutation(A.m).astype(np.int32)
+    rp, ci, va = api.permute_csr(A.rowptr, A.col, A.val, q)
+    return M.CSR(A.m, A.n, rp, ci, va, A.name + "_scrambled")
+
+
+def _bandwidth(a):
+    rows = np.repeat(np.arange(a.m), np.diff(a.rowptr))
+    return int(np.abs(rows - a.col).max()) if a.nnz else 0
+
+
+def test_permute_csr_is_the_permuted_operator(libpath):
+    A = M.uniform_random(300, 300, 7, seed=5)            # duplicates inside rows included
+    rng = np.random.default_rng(1)
+    index = rng.permutation(A.m).astype(np.int32)
+    rp, ci, va = api.permute_csr(A.rowptr, A.col, A.val, index)
+    S = sp.csr_matrix((A.val, A.col, A.rowptr), shape=(A.m, A.n))       # (sums duplicates)
+    S2 = sp.csr_matrix((va, ci, rp), shape=(A.m, A.n))
+    P = sp.csr_matrix((np.ones(A.m), (np.arange(A.m), index)), shape=(A.m, A.m))   # row i of P picks row index[i]
+    assert abs(S2 - P @ S @ P.T).max() == 0.0
+    for i in range(A.m):                                  # columns ascending inside every row
+        assert (np.diff(ci[rp[i]:rp[i + 1]]) >= 0).all()
+    assert np.array_equal(np.diff(rp), np.diff(A.rowptr)[index])
+    # not a permutation / not square: refused
+    bad = index.copy()
+    bad[0] = bad[1]
+    with pytest.raises(ValueError):
+        api.permute_csr(A.rowptr, A.col, A.val, bad)
+    R = M.uniform_random(50, 80, 3, seed=2)
+    with pytest.raises(ValueError):
+        api.permute_csr(R.rowptr, R.col, R.val, np.arange(50, dtype=np.int32))
+
+
+@pytest.mark.parametrize("make", [lambda: M.laplacian2d(64), lambda: M.stencil27(12)])
+def test_rcm_restores_the_locality_of_a_scrambled_mesh(libpath, make):
+    A = make()
+    B = _scramble(A, 7)
+    index = api.reorder(B.rowptr, B.col)
+    assert np.array_equal(np.sort(index), np.arange(B.m))
+    rp, ci, va = api.permute_csr(B.rowptr, B.col, B.val, index)
+    C = M.CSR(B.m, B.n, rp, ci, va)
+    bw_natural, bw_scrambled, bw_rcm = _bandwidth(A), _bandwidth(B), _bandwidth(C)
+    assert bw_scrambled > 10 * bw_natural                 # the scrambling really destroyed the numbering
+    assert bw_rcm <= 3 * bw_natural, (bw_natural, bw_scrambled, bw_rcm)
+
+
+def test_reference_protocol_on_the_reordered_matrix_reproduces_y(libpath, port):
+    A = _scramble(M.laplacian2d(40), 3)
+    index = api.reorder(A.rowptr, A.col)
+    rp, ci, va = api.permute_csr(A.rowptr, A.col, A.val, index)
+    x = M.make_x(A.n, 9, np.float64)
+    y_ref = port.spmv_serial(A.rowptr, A.col, A.val, x)
+    xx = x[index]                                          # test_spmv.c:95-98
+    yy = port.spmv_serial(rp, ci, va, xx)
+    y = np.empty_like(yy)
+    y[index] = yy                                          # test_spmv.c:130-133
+    tol = 8 * np.finfo(np.float64).eps * port.row_abs_sum(A.rowptr, A.col, A.val, x)
+    assert (np.abs(y - y_ref) <= tol).all()
+
+
+def test_reorder_handles_unsymmetric_patterns_empty_rows_and_components(libpath):
+    A = M.from_row_lengths([0, 3, 0, 0, 5, 1, 0, 2] * 50, 400)     # unsymmetric, many empty rows, disconnected
+    index = api.reorder(A.rowptr, A.col)
+    assert np.array_equal(np.sort(index), np.arange(A.m))
+    rp, ci, va = api.permute_csr(A.rowptr, A.col, A.val, index)
+    assert rp[-1] == A.nnz and np.array_equal(np.sort(va), np.sort(A.val))
+    Z = M.from_row_lengths([0] * 10, 10)
+    assert np.array_equal(np.sort(api.reorder(Z.rowptr, Z.col)), np.arange(10))
