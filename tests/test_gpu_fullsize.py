@@ -35,18 +35,14 @@ CONFIGS = {
     "c2": lambda: (api.gen_uniform(1 << 24, 1 << 24, 32, M.SEED_C2, 0, False, 8), M.SEED_C2),
     "c3": lambda: (api.gen_rmat(24, 16, M.SEED_C3, 4), M.SEED_C3),
     "c4": lambda: (api.gen_stencil27(256, 256, 256, 8), 4),
-    # one GPU's share of C5 at 8 GPUs: rows [0, 2^25) of the 2^28-column matrix, 2^29 non-zeros, x = 2 GiB -- the one
-    # shape on which the AUTOMATIC band-segment layout (48 column bands, 64-bit row masks) and 2^28-wide column indices are exercised
-    "c5shard": lambda: (api.gen_uniform(1 << 25, 1 << 28, 16, M.SEED_C5, 0, False, 8), M.SEED_C5),
 }
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_full_size_parity_against_torch_and_properties(libpath, name):
+def check_full_size(name, make):
     import torch
     if torch.cuda.get_device_properties(0).total_memory < 60e9:
         pytest.skip("needs a B200-class device (full-size matrices + torch temporaries)")
-    A, seed = CONFIGS[name]()
+    A, seed = make()
     tdt = torch.float64 if A.size == 8 else torch.float32
     vstr = "<f8" if A.size == 8 else "<f4"
     eps = float(torch.finfo(tdt).eps)
@@ -95,33 +91,6 @@ def test_full_size_parity_against_torch_and_properties(libpath, name):
     A.destroy()
 
 
-def test_full_size_c1_against_the_live_reference(libpath, port):
-    """BASELINE.json configs[0] at its full size (5-point Laplacian on a 1024 x 1024 grid, fp64): Method_Serial on
-    the GPU is bit-identical to the compiled reference's Method_Serial; every other method meets the per-row bound
-    against it and against the extended-precision sum; fp32 likewise."""
-    from conftest import bits_equal
-    from oracle import oracle as O
-    a64 = M.laplacian2d(1024)
-    for dt in (np.float64, np.float32):
-        a = a64.astype(dt)
-        x = M.make_x(a.n, 1, dt)
-        if O.have_reference():
-            y_ref = O.Reference().serial(a.rowptr, a.col, a.val, x)
-        else:
-            y_ref = port.spmv_serial(a.rowptr, a.col, a.val, x)
-        y_ex = port.spmv_exact(a.rowptr, a.col, a.val, x)
-        eps = np.finfo(dt).eps
-        tol = 8 * eps * port.row_abs_sum(a.rowptr, a.col, a.val, x)
-        for method in range(7):
-            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val, method, nthreads=8)
-            y = np.full(a.m, np.nan, dtype=dt)
-            h.spmv(x, y)
-            tag = f"c1/{dt.__name__}/{api.METHOD_NAMES[method]}[{h.kernel}]"
-            if method == api.Method_Serial:
-                assert bits_equal(y, y_ref), tag
-            assert (np.abs(y.astype(np.float64) - y_ref.astype(np.float64)) <= tol).all(), tag
-            assert (np.abs(y.astype(np.float64) - y_ex.astype(np.float64)) <= tol + 0.5 * eps * np.abs(y_ex)).all(), tag
-            y2 = np.full(a.m, np.nan, dtype=dt)
-            h.spmv(x, y2)
-            assert bits_equal(y, y2), tag
-            h.destroy()
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_full_size_parity_against_torch_and_properties(libpath, name):
+    check_full_size(name, CONFIGS[name])
