@@ -10,11 +10,13 @@ L2-warm, C3, C4, the C5 shard) and, with --c5, the full C5 power-method iteratio
 baseline of the multi-GPU record).
 
 N > 1 (strong scaling, `"scaling": "strong"`): a step is one iteration x <- A x of the power method on the SAME square
-C2 matrix, row-sharded over the N ranks by equal nnz (the reference's splitter), INCLUDING the y -> x exchange.  The
-headline uses the pipelined loop (spmv_b200/multigpu.py: the exchange of iteration k overlaps the band-staged SpMV of
-iteration k+1); the plain loop (SpMV, then ncclAllGather, timed separately) and the SpMV alone are reported next to
-it, bitwise equality of the two loops is asserted.  `c5` holds the same three numbers for BASELINE.json configs[4]
-(uniform-random 2^28 x 2^28, 16 nnz/row, 50 iterations) at this N.
+C2 matrix, row-sharded over the N ranks by equal nnz (the reference's splitter), INCLUDING the y -> x exchange.  Three
+loops run on the same handles (spmv_b200/multigpu.py) and must agree bit for bit: the plain loop (SpMV, then
+ncclAllGather, timed separately -- the reported baseline), the pipelined loop over NCCL send/recv, and the pipelined
+loop whose exchange runs on the copy engines (peer DMA + stream flags) under the band-staged SpMV of the next
+iteration; `value` comes from the fastest of them, `power_method` holds all their numbers (SpMV alone, exchange alone,
+exposed exchange).  `c5` holds the same record for BASELINE.json configs[4] (uniform-random 2^28 x 2^28, 16 nnz/row,
+50 iterations) at this N.  Every multi-GPU leg runs under a watchdog (see Watchdog).
 
 Other workloads (`--workload c1|c3|c4|c5shard`) time the remaining configurations as the primary one (single GPU).
 `--also` names further methods timed after the primary one; their numbers land in "methods".
