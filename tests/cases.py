@@ -36,3 +36,34 @@ def all_cases():
     d = dict(GOLDEN_CASES)
     d.update(EXTRA_CASES)
     return d
+
+
+def expected_band_segments(a, bands, with_values=False):
+    """numpy restatement of the band-segment layout (band_seg.cuh): entries stably bucketed by col // band_cols,
+    band starts aligned to 4 slots, bit 31 of the column index marks the last entry of a (band, row) run."""
+    bc = -(-a.n // bands)
+    rows = np.repeat(np.arange(a.m, dtype=np.int64), np.diff(a.rowptr))
+    band = np.minimum(a.col // bc, bands - 1)
+    order = np.argsort(band, kind="stable")
+    cnt = np.bincount(band, minlength=bands).astype(np.int64)
+    ptr = np.zeros(bands + 1, dtype=np.int64)
+    for b in range(bands):
+        ptr[b + 1] = (ptr[b] + cnt[b] + 3) & ~3
+    col = np.zeros(int(ptr[bands]), dtype=np.uint32)
+    srows, sband = rows[order], band[order]
+    last = np.ones(len(order), dtype=bool)
+    if len(order) > 1:
+        last[:-1] = (srows[1:] != srows[:-1]) | (sband[1:] != sband[:-1])
+    sorted_start = np.concatenate([[0], np.cumsum(cnt)])
+    for b in range(bands):
+        lo, hi = int(sorted_start[b]), int(sorted_start[b + 1])
+        col[int(ptr[b]):int(ptr[b]) + hi - lo] = a.col[order[lo:hi]].astype(np.uint32) | (last[lo:hi].astype(np.uint32) << 31)
+    mask = np.zeros(a.m, dtype=np.uint64)
+    np.bitwise_or.at(mask, rows, np.uint64(1) << band.astype(np.uint64))
+    if with_values:
+        val = np.zeros(int(ptr[bands]), dtype=a.val.dtype)
+        for b in range(bands):
+            lo, hi = int(sorted_start[b]), int(sorted_start[b + 1])
+            val[int(ptr[b]):int(ptr[b]) + hi - lo] = a.val[order[lo:hi]]
+        return bc, ptr.astype(np.int32), cnt.astype(np.int32), col, mask, int(last.sum()), val
+    return bc, ptr.astype(np.int32), cnt.astype(np.int32), col, mask, int(last.sum())
