@@ -79,3 +79,34 @@ def test_reorder_handles_unsymmetric_patterns_empty_rows_and_components(libpath)
     assert rp[-1] == A.nnz and np.array_equal(np.sort(va), np.sort(A.val))
     Z = M.from_row_lengths([0] * 10, 10)
     assert np.array_equal(np.sort(api.reorder(Z.rowptr, Z.col)), np.arange(10))
+
+
+def test_create_with_option_reorder_fills_the_public_fields_even_without_a_gpu(libpath):
+    """The host half of create runs before anything touches the device: on a box without a GPU the handle ends up
+    unusable (`ok` == 0, no CPU fallback), but handle->index / Level_3_opt_used are already what the reference's
+    protocol expects, and clear / destroy release the permutation."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("the GPU half is covered by tests/test_gpu_zz2_create_options.py")
+    a = _scramble(M.laplacian2d(160), 11)                 # 25 600 rows, 127 360 non-zeros: above the reference's thresholds
+    want = api.reorder(a.rowptr, a.col)
+    api.set_option("reorder", 1)
+    try:
+        h = api.spmv_create_handle_all_in_one(a.m, a.n, a.rowptr, a.col, a.val, 4, api.Method_Parallel, 8)
+        small = M.laplacian2d(48)
+        h2 = api.spmv_create_handle_all_in_one(small.m, small.n, small.rowptr, small.col, small.val, 4, api.Method_Parallel, 8)
+    finally:
+        api.set_option("reorder", 0)
+    api.clear_error()
+    s = h.contents
+    assert api.lib().spmv_b200_info(h, b"ok") == 0
+    assert s.Level_3_opt_used == 1 and s.index
+    index = np.ctypeslib.as_array(C.cast(s.index, C.POINTER(C.c_int)), shape=(a.m + 1,)).copy()
+    assert np.array_equal(index[:a.m], want) and index[a.m] == a.m
+    assert h2.contents.Level_3_opt_used == 0 and not h2.contents.index     # below the thresholds: untouched
+    api.spmv_clear_handle(h)
+    assert h.contents.Level_3_opt_used == 0 and not h.contents.index
+    api.spmv_destory_handle(h)
+    api.spmv_destory_handle(h2)
+    api.clear_error()
