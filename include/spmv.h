@@ -22,8 +22,9 @@
  *     (spmv_b200_info(h, "values_snapshotted") == 1 says so);
  *   - fp32 Method_CSR5SPMV is a real CSR5 and handle->spmvMethod stays Method_CSR5SPMV (the reference runs SELL and
  *     stores Method_SellCSigma, common.c:177-180);
- *   - ONE spmv() in flight per handle: the handle owns staging buffers, partial-sum arrays and events, so calls on
- *     the same handle must not overlap (different handles are independent);
+ *   - the handle owns staging buffers, partial-sum arrays and events: calls on the SAME handle from several threads are
+ *     serialised by a per-handle mutex (their launches reach the handle's stream call after call); two streams on one
+ *     handle are not supported -- use one handle per stream (different handles are independent);
  *   - a pageable HOST x or y of at least 1 MiB that is passed twice in a row is page-locked in place so that its
  *     copies run at PCIe speed, and released when the caller switches buffers or clears / destroys the handle:
  *     do not free such a buffer while the handle is alive (SPMV_B200_PIN_HOST=0 switches this off).

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #define SPMV_B200_NO_HOST_HEADERS 1
 #include "../../include/spmv_b200.h"
@@ -36,6 +37,10 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 // ------------------------------------------------------------------------------------------------
 struct DeviceState {
     uint32_t magic = 0x5b200a11u;
+    // The handle owns staging buffers, partial-sum arrays and events (the reference's handle is read-only in spmv()
+    // for most methods, SURVEY 8b "Threading"): calls on ONE handle from several threads are serialised here, so
+    // that their launches reach the stream call after call instead of interleaved
+    std::mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;  // legacy default stream unless spmv_b200_set_stream
     int m = 0, n = 0, nnz = 0;

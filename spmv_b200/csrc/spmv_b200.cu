@@ -1361,6 +1361,7 @@ void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *Ro
     (void)m; (void)RowPtr; (void)ColIdx; (void)Matrix_Val;  // the handle owns the device copies
     DeviceState *st = state_of(handle);  // NULL handle: silent return (common.c:285)
     if (!st || !st->ok || !Vector_Val_Y || (!Vector_Val_X && st->n > 0)) return;
+    std::lock_guard<std::mutex> lock(st->mu);
     DeviceGuard guard(st->device);
     const bool x_dev = is_device_ptr(Vector_Val_X), y_dev = is_device_ptr(Vector_Val_Y);
     const void *xd = Vector_Val_X;
@@ -1422,7 +1423,10 @@ unsigned long long spmv_b200_launch_count(void) { return g_launches.load(); }
 
 void spmv_b200_set_stream(spmv_Handle_t handle, void *cuda_stream)
 {
-    if (DeviceState *st = state_of(handle)) st->stream = (cudaStream_t)cuda_stream;
+    if (DeviceState *st = state_of(handle)) {
+        std::lock_guard<std::mutex> lock(st->mu);
+        st->stream = (cudaStream_t)cuda_stream;
+    }
 }
 
 void spmv_b200_sync(spmv_Handle_t handle)
@@ -1437,6 +1441,7 @@ int spmv_b200_set_y_peers(spmv_Handle_t handle, int count, void *const *device_p
 {
     DeviceState *st = state_of(handle);
     if (!st || count < 0 || count > kMaxPeers || (count > 0 && !device_ptrs)) return -1;
+    std::lock_guard<std::mutex> lock(st->mu);
     st->n_peers = count;
     for (int i = 0; i < kMaxPeers; ++i) st->peers[i] = i < count ? device_ptrs[i] : nullptr;
     return 0;
@@ -1477,6 +1482,7 @@ int spmv_b200_spmv_bands(spmv_Handle_t handle, int band_first, int band_count, c
     if (!stageable(st) || band_first < 0 || band_count < 0 || band_first + band_count > st->x_bands) return -1;
     if (band_count == 0) return 0;
     if (!is_device_ptr(x_device)) { set_error("spmv_b200_spmv_bands: x must be a device pointer"); return -1; }
+    std::lock_guard<std::mutex> lock(st->mu);
     DeviceGuard guard(st->device);
     bool ok;
     if (st->kernel == SPMV_B200_KERNEL_BAND_SEG) {
@@ -1521,6 +1527,7 @@ int spmv_b200_spmv_finish(spmv_Handle_t handle, void *y_device)
     DeviceState *st = state_of(handle);
     if (!stageable(st)) return -1;
     if (!is_device_ptr(y_device)) { set_error("spmv_b200_spmv_finish: y must be a device pointer"); return -1; }
+    std::lock_guard<std::mutex> lock(st->mu);
     DeviceGuard guard(st->device);
     bool ok;
     if (st->kernel == SPMV_B200_KERNEL_BAND_SEG)
