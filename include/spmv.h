@@ -18,8 +18,8 @@
  *
  * Deviations a client can observe (everything else follows the reference):
  *   - the matrix VALUES are snapshotted at create (the reference re-reads the caller's arrays on every call for
- *     Serial / Parallel / Balanced*): after changing Matrix_Val, clear and re-create the handle
- *     (spmv_b200_info(h, "values_snapshotted") == 1 says so);
+ *     Serial / Parallel / Balanced*): after changing Matrix_Val call spmv_b200_update_values() (spmv_b200.h) or clear
+ *     and re-create the handle (spmv_b200_info(h, "values_snapshotted") == 1 says so);
  *   - fp32 Method_CSR5SPMV is a real CSR5 and handle->spmvMethod stays Method_CSR5SPMV (the reference runs SELL and
  *     stores Method_SellCSigma, common.c:177-180);
  *   - the handle owns staging buffers, partial-sum arrays and events: calls on the SAME handle from several threads are

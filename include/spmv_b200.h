@@ -28,6 +28,14 @@ SPMV_B200_API int spmv_b200_version(void);
 SPMV_B200_API const char *spmv_b200_last_error(void);
 SPMV_B200_API void spmv_b200_clear_error(void);
 
+/* ---- refreshing the values -------------------------------------------------------------------------
+ * spmv() ignores its Matrix_Val argument: the values are part of the device layout built at create (the reference
+ * re-reads the caller's array on every call for Serial / Parallel / Balanced*).  After changing values on a FIXED
+ * pattern call spmv_b200_update_values(handle, Matrix_Val): the handle is rebuilt in place from the RowPtr / ColIdx
+ * it borrowed at create and the values given (NULL = re-read the array given at create), same method, precision and
+ * stream.  Costs one create.  Returns 0, or -1 (spmv_b200_last_error()). */
+SPMV_B200_API int spmv_b200_update_values(spmv_Handle_t handle, void *Matrix_Val);
+
 /* ---- streams -----------------------------------------------------------------------------------
  * spmv() with HOST x/y is synchronous (reference semantics).  With DEVICE x/y it is enqueued on the
  * handle's stream (default: the legacy default stream 0) and returns immediately. */

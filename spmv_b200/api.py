@@ -39,7 +39,7 @@ EXPORTED_FUNCTIONS = [
     "spmv_b200_set_y_peers", "spmv_b200_ipc_export", "spmv_b200_ipc_open", "spmv_b200_ipc_close",
     "spmv_b200_recommend_method", "spmv_b200_bands", "spmv_b200_band_columns", "spmv_b200_spmv_bands",
     "spmv_b200_spmv_finish", "spmv_b200_memcpy_async", "spmv_b200_stream_write32", "spmv_b200_stream_wait32_geq",
-    "spmv_b200_reorder", "spmv_b200_permute_csr"]
+    "spmv_b200_reorder", "spmv_b200_permute_csr", "spmv_b200_update_values"]
 EXPORTED_DATA = ["Methods_names", "Vectorized_names", "funcNames"]
 
 
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
     L.spmv_b200_band_columns.argtypes = [spmv_Handle_t, i, C.POINTER(ll), C.POINTER(ll)]
     L.spmv_b200_spmv_bands.argtypes = [spmv_Handle_t, i, i, vp]
     L.spmv_b200_spmv_finish.argtypes = [spmv_Handle_t, vp]
+    L.spmv_b200_update_values.argtypes = [spmv_Handle_t, vp]
     L.spmv_b200_reorder.argtypes = [i, vp, vp, vp]
     L.spmv_b200_permute_csr.argtypes = [i, vp, vp, vp, ul, vp, vp, vp, vp]
     L.spmv_b200_memcpy_async.argtypes = [vp, vp, C.c_size_t, vp]
@@ -226,6 +227,13 @@ class Handle:
         arr = (C.c_void_p * max(len(ptrs), 1))(*[int(p) for p in ptrs])
         if lib().spmv_b200_set_y_peers(self.h, len(ptrs), arr) != 0:
             raise ValueError("set_y_peers: at most 8 destinations")
+
+    def update_values(self, Matrix_Val=None):
+        """Rebuild the device layout with new values on the same pattern (spmv_b200_update_values)."""
+        if Matrix_Val is not None:
+            self.keep = (self.keep[0], self.keep[1], Matrix_Val)
+        if lib().spmv_b200_update_values(self.h, _addr(Matrix_Val) if Matrix_Val is not None else None) != 0:
+            raise RuntimeError("spmv_b200_update_values failed: " + last_error())
 
     def bands(self) -> int:
         """Column bands that can be staged one by one (1: use spmv())."""

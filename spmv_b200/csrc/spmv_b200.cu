@@ -840,6 +840,7 @@ static int auto_pick_method(DeviceState *st)
 static bool build_state(DeviceState *st, spmv_Handle *h, int m, int n, int *RowPtr, int *ColIdx, void *Val,
                         int method)
 {
+    st->requested = method;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -1302,18 +1303,10 @@ const char *Vectorized_names[] = {"VECTOR_NONE", "VECTOR_AVX2", "VECTOR_AVX512"}
 // ================================================================================================
 // the four drop-in entry points
 // ================================================================================================
-void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASIC_INT_TYPE n,
-                                   BASIC_INT_TYPE *RowPtr, BASIC_INT_TYPE *ColIdx, void *Matrix_Val,
-                                   BASIC_SIZE_TYPE nthreads, SPMV_METHODS Function, BASIC_SIZE_TYPE size,
-                                   VECTORIZED_WAY vectorizedWay, const char *MtxToken)
+// everything create does to an initialised public struct (shared by create and spmv_b200_update_values)
+static void create_into(spmv_Handle *h, BASIC_INT_TYPE m, BASIC_INT_TYPE n, BASIC_INT_TYPE *RowPtr, BASIC_INT_TYPE *ColIdx,
+                        void *Matrix_Val, BASIC_SIZE_TYPE nthreads, int method, BASIC_SIZE_TYPE size, VECTORIZED_WAY vectorizedWay)
 {
-    (void)MtxToken;  // only keys the reference's compiled-out METIS cache (common.c:152-154)
-    if (!Handle) return;
-    spmv_Handle *h = (spmv_Handle *)malloc(sizeof(spmv_Handle));  // freed by spmv_destory_handle
-    *Handle = h;
-    if (!h) return;
-    handle_init(h);
-    int method = (int)Function;
     if (method < (int)Method_Serial || method >= (int)Method_Total_Size) method = Method_Serial;  // common.c:136
     h->nthreads = nthreads;  // handle_init_common_parameters, common.c:74-83
     h->vectorizedWay = vectorizedWay;
@@ -1353,6 +1346,20 @@ void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASI
         free(index);
     }
     st->ok = build_state(st, h, m, n, RowPtr, ColIdx, Matrix_Val, method);
+}
+
+void spmv_create_handle_all_in_one(spmv_Handle_t *Handle, BASIC_INT_TYPE m, BASIC_INT_TYPE n,
+                                   BASIC_INT_TYPE *RowPtr, BASIC_INT_TYPE *ColIdx, void *Matrix_Val,
+                                   BASIC_SIZE_TYPE nthreads, SPMV_METHODS Function, BASIC_SIZE_TYPE size,
+                                   VECTORIZED_WAY vectorizedWay, const char *MtxToken)
+{
+    (void)MtxToken;  // only keys the reference's compiled-out METIS cache (common.c:152-154)
+    if (!Handle) return;
+    spmv_Handle *h = (spmv_Handle *)malloc(sizeof(spmv_Handle));  // freed by spmv_destory_handle
+    *Handle = h;
+    if (!h) return;
+    handle_init(h);
+    create_into(h, m, n, RowPtr, ColIdx, Matrix_Val, nthreads, (int)Function, size, vectorizedWay);
 }
 
 void spmv(const spmv_Handle_t handle, BASIC_INT_TYPE m, const BASIC_INT_TYPE *RowPtr,
@@ -1411,6 +1418,27 @@ void spmv_destory_handle(spmv_Handle_t this_handle)  // reference common.c:54-61
     if (!this_handle) return;
     spmv_clear_handle(this_handle);
     free(this_handle);
+}
+
+// The reference re-reads the caller's Matrix_Val on every spmv() (Serial / Parallel / Balanced*); here the values are
+// part of the device layout.  A client that changes values on a fixed pattern calls this instead of destroy + create:
+// the handle is rebuilt in place from its own borrowed RowPtr / ColIdx, the values given here (NULL: the Matrix_Val
+// it was created with, re-read), the same method, precision, nthreads and stream.  Cost: one create.
+int spmv_b200_update_values(spmv_Handle_t handle, void *Matrix_Val)
+{
+    DeviceState *st = state_of(handle);
+    if (!st || !st->ok) return -1;  // (a handle whose create failed has nothing to refresh)
+    const int m = st->m, n = st->n, method = st->requested;
+    cudaStream_t stream = st->stream;
+    BASIC_INT_TYPE *rp = handle->RowPtr, *ci = handle->ColIdx;
+    void *va = Matrix_Val ? Matrix_Val : handle->Matrix_Val;
+    const BASIC_SIZE_TYPE nthreads = handle->nthreads, size = handle->data_size;
+    const VECTORIZED_WAY vw = handle->vectorizedWay;
+    spmv_clear_handle(handle);
+    create_into(handle, m, n, rp, ci, va, nthreads, method, size, vw);
+    DeviceState *fresh = state_of(handle);
+    if (fresh) fresh->stream = stream;
+    return fresh && fresh->ok ? 0 : -1;
 }
 
 // ================================================================================================

@@ -180,3 +180,36 @@ def test_unmodified_sample_driver_takes_its_index_branch(libpath, tmp_path):
     assert len(rows) == 6 and "[spmv_b200]" not in r.stderr, (r.stdout, r.stderr)
     for o in rows:
         assert int(o[4]) == a.nnz and float(o[5]) == 0.0, o
+
+
+# ------------------------------------------------------------------------------------------------
+# spmv_b200_update_values: new values on a fixed pattern
+# ------------------------------------------------------------------------------------------------
+def test_update_values_rebuilds_the_layout_in_place(libpath, port):
+    """The values are part of the device layout (spmv() ignores Matrix_Val, unlike the reference); after changing them
+    the client calls spmv_b200_update_values().  Checked for layouts that copy the values (SELL, CSR5, band-major,
+    band segments) and for the plain CSR kernels."""
+    a = M.uniform_random(6000, 6000, 24, seed=9)
+    x = M.make_x(a.n, 3, np.float64)
+    new_val = (a.val * 0.5 + 0.25).copy()
+    want = port.spmv_exact(a.rowptr, a.col, new_val, x)
+    tol = 8 * np.finfo(np.float64).eps * port.row_abs_sum(a.rowptr, a.col, new_val, x) + 0.5 * np.finfo(np.float64).eps * np.abs(want)
+    for method, opt in ((api.Method_Parallel, None), (api.Method_SellCSigma, None), (api.Method_CSR5SPMV, None),
+                        (api.Method_Parallel, ("x_bands", 3)), (api.Method_Balanced2, ("seg_bands", 5))):
+        if opt:
+            api.set_option(*opt)
+        try:
+            h = api.Handle(a.m, a.n, a.rowptr, a.col, a.val.copy(), method)
+            kernel = h.kernel
+            y0 = np.full(a.m, np.nan)
+            h.spmv(x, y0)
+            h.update_values(new_val)                      # (the option is still set: the rebuilt layout is the same kind)
+        finally:
+            if opt:
+                api.set_option(opt[0], 0)
+        assert h.kernel == kernel, (method, opt)
+        y = np.full(a.m, np.nan)
+        h.spmv(x, y)
+        assert (np.abs(y - want) <= tol).all(), (api.METHOD_NAMES[method], opt)
+        assert not np.array_equal(y, y0)
+        h.destroy()

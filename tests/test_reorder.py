@@ -110,3 +110,16 @@ def test_create_with_option_reorder_fills_the_public_fields_even_without_a_gpu(l
     api.spmv_destory_handle(h)
     api.spmv_destory_handle(h2)
     api.clear_error()
+
+
+def test_update_values_on_an_unusable_handle_fails_cleanly(libpath):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("the working case is covered by tests/test_gpu_zz2_create_options.py")
+    a = M.laplacian2d(20)
+    h = api.spmv_create_handle_all_in_one(a.m, a.n, a.rowptr, a.col, a.val, 1, api.Method_SellCSigma, 8)
+    assert api.lib().spmv_b200_update_values(h, a.val.ctypes.data) == -1      # no device: nothing to refresh, nothing touched
+    assert api.lib().spmv_b200_info(h, b"requested") == api.Method_SellCSigma and api.lib().spmv_b200_info(h, b"ok") == 0
+    assert api.lib().spmv_b200_update_values(None, None) == -1
+    api.spmv_destory_handle(h)
+    api.clear_error()
