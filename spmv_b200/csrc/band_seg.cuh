@@ -2,7 +2,7 @@
 //
 // The band-major copy of csr_kernels.cuh stores band b of row r as virtual row b*m + r of a CSR.  When x is so
 // large that the number of bands K approaches the mean row length (BASELINE.json config C5: 16 non-zeros per
-// row, x = 2 GiB => K = 32, 0.5 non-zeros per row and band) the K*m+1 virtual row pointers outweigh the matrix,
+// row, x = 2 GiB => K = 48, a third of a non-zero per row and band) the K*m+1 virtual row pointers outweigh the matrix,
 // and a y vector that is swept once per band (round 1's COO bands) costs 2*K*m*sizeof(val) bytes of DRAM traffic.
 // Here the matrix is the list of its entries, stably bucketed by col / band_cols and sorted by row inside a band;
 // a maximal run of entries of one row inside one band is a SEGMENT, marked by bit 31 of the column index of its
